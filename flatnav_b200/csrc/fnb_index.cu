@@ -1,0 +1,568 @@
+// Host side of libflatnav_b200.so: index loader (reference cereal layout -> HBM arrays), search
+// dispatch and the C ABI declared in include/flatnav_b200.h.  No CPU fallback anywhere: every compute
+// entry point requires a CUDA device.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/flatnav_b200.h"
+#include "fnb_internal.h"
+
+namespace fnb {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+
+#define CU(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e__ = (call);                                                                      \
+    if (e__ != cudaSuccess)                                                                        \
+      return fail(FNB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+// ---- layout kernels -------------------------------------------------------------------------------
+// One warp per node; byte-wise so that any data_size / node_size (including unaligned ones) is handled.
+// Reference node layout: [vector (data_size B) | M x u32 links | i32 label]  (Index.h:555-573).
+__global__ void deinterleave_kernel(const unsigned char* __restrict__ blob, uint64_t n_nodes, uint64_t node_size,
+                                    uint32_t data_size, uint32_t M, uint32_t stride_bytes,
+                                    unsigned char* __restrict__ vec, uint32_t* __restrict__ adj,
+                                    int32_t* __restrict__ labels) {
+  const uint64_t warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  for (uint64_t n = (((uint64_t)blockIdx.x * blockDim.x) + threadIdx.x) >> 5; n < n_nodes; n += warps) {
+    const unsigned char* src = blob + n * node_size;
+    unsigned char* dst = vec + n * stride_bytes;
+    for (uint32_t b = lane; b < stride_bytes; b += 32) dst[b] = b < data_size ? src[b] : (unsigned char)0;
+    const unsigned char* ls = src + data_size;
+    for (uint32_t j = lane; j <= M; j += 32) {
+      uint32_t v = (uint32_t)ls[4 * j] | ((uint32_t)ls[4 * j + 1] << 8) | ((uint32_t)ls[4 * j + 2] << 16) |
+                   ((uint32_t)ls[4 * j + 3] << 24);
+      if (j < M)
+        adj[n * M + j] = v;
+      else
+        labels[n] = (int32_t)v;
+    }
+  }
+}
+
+__global__ void interleave_kernel(unsigned char* __restrict__ blob, uint64_t n_nodes, uint64_t node_size,
+                                  uint32_t data_size, uint32_t M, uint32_t stride_bytes,
+                                  const unsigned char* __restrict__ vec, const uint32_t* __restrict__ adj,
+                                  const int32_t* __restrict__ labels) {
+  const uint64_t warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  for (uint64_t n = (((uint64_t)blockIdx.x * blockDim.x) + threadIdx.x) >> 5; n < n_nodes; n += warps) {
+    unsigned char* dst = blob + n * node_size;
+    const unsigned char* src = vec + n * stride_bytes;
+    for (uint32_t b = lane; b < data_size; b += 32) dst[b] = src[b];
+    unsigned char* ls = dst + data_size;
+    for (uint32_t j = lane; j <= M; j += 32) {
+      uint32_t v = j < M ? adj[n * M + j] : (uint32_t)labels[n];
+      ls[4 * j] = (unsigned char)v;
+      ls[4 * j + 1] = (unsigned char)(v >> 8);
+      ls[4 * j + 2] = (unsigned char)(v >> 16);
+      ls[4 * j + 3] = (unsigned char)(v >> 24);
+    }
+  }
+}
+
+// every link of a live node must point at a live node (Appendix A.6 of SURVEY.md)
+__global__ void validate_links_kernel(const uint32_t* __restrict__ adj, uint64_t n_links, uint32_t n_nodes,
+                                      unsigned int* __restrict__ bad) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_links; i += stride)
+    if (adj[i] >= n_nodes) atomicAdd(bad, 1u);
+}
+
+// ---- header ------------------------------------------------------------------------------------------
+// cereal BinaryOutputArchive of Index::serialize (Index.h:134-141): int32 data_type, u64 M, u64 data_size,
+// u64 node_size, u64 max_node_count, u64 cur_num_nodes, then the distance object's (u64 dimension,
+// u64 data_size) (SquaredL2Distance.h:54-57 / InnerProductDistance.h:53-56); little endian, no padding.
+static int parse_header(const unsigned char* p, size_t nbytes, int metric, int expect_dtype, Header* h) {
+  if (nbytes < FNB_HEADER_BYTES) return fail(FNB_ERR_FORMAT, "index file shorter than the 60-byte header");
+  if (metric != FNB_METRIC_L2 && metric != FNB_METRIC_IP) return fail(FNB_ERR_INVALID_ARG, "unknown metric %d", metric);
+  int32_t dt;
+  uint64_t v[7];
+  memcpy(&dt, p, 4);
+  memcpy(v, p + 4, 56);
+  h->data_type = dt;
+  h->metric = metric;
+  h->M = v[0];
+  h->data_size = v[1];
+  h->node_size = v[2];
+  h->max_nodes = v[3];
+  h->cur_nodes = v[4];
+  h->dim = v[5];
+  uint64_t es = dt == FNB_DTYPE_FLOAT32 ? 4 : (dt == FNB_DTYPE_UINT8 || dt == FNB_DTYPE_INT8) ? 1 : 0;
+  if (es == 0) return fail(FNB_ERR_FORMAT, "unsupported data_type %d in index header", dt);
+  if (expect_dtype != FNB_DTYPE_ANY && expect_dtype != dt)
+    return fail(FNB_ERR_FORMAT, "index holds data_type %d but %d was requested", dt, expect_dtype);
+  if (v[6] != h->data_size || h->dim * es != h->data_size)
+    return fail(FNB_ERR_FORMAT, "header inconsistent: dim=%llu data_size=%llu/%llu", (unsigned long long)h->dim,
+                (unsigned long long)h->data_size, (unsigned long long)v[6]);
+  if (h->node_size != h->data_size + 4 * h->M + 4)
+    return fail(FNB_ERR_FORMAT, "header inconsistent: node_size %llu != data_size + 4M + 4",
+                (unsigned long long)h->node_size);
+  if (h->cur_nodes > h->max_nodes) return fail(FNB_ERR_FORMAT, "cur_num_nodes > max_node_count");
+  if (h->M == 0 || h->dim == 0) return fail(FNB_ERR_FORMAT, "M and dim must be positive");
+  if (h->max_nodes >= (1ull << 31)) return fail(FNB_ERR_UNSUPPORTED, "more than 2^31 nodes");
+  if (nbytes < FNB_HEADER_BYTES + h->node_size * h->max_nodes)
+    return fail(FNB_ERR_FORMAT, "index file truncated: %zu bytes, need %llu", nbytes,
+                (unsigned long long)(FNB_HEADER_BYTES + h->node_size * h->max_nodes));
+  if (fnb_nchunks(h->data_size) > FNB_MAX_CHUNKS)
+    return fail(FNB_ERR_UNSUPPORTED, "vector of %llu bytes exceeds the %u-byte limit of the kernels",
+                (unsigned long long)h->data_size, FNB_MAX_CHUNKS * FNB_CHUNK_BYTES);
+  return FNB_OK;
+}
+
+static int upload_replica(const Header& h, const unsigned char* blob, int device, Replica* r) {
+  CU(cudaSetDevice(device));
+  r->device = device;
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10)
+    return fail(FNB_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device,
+                prop.major, prop.minor);
+  r->num_sms = prop.multiProcessorCount;
+  const uint32_t nchunks = fnb_nchunks(h.data_size);
+  const uint32_t stride = fnb_stride_chunks(nchunks);
+  const uint64_t n = h.cur_nodes ? h.cur_nodes : 1;
+  const uint64_t blob_bytes = h.node_size * h.cur_nodes;
+  unsigned char* d_blob = nullptr;
+  CU(cudaMalloc(&r->vec, n * stride * FNB_CHUNK_BYTES));
+  CU(cudaMalloc(&r->adj, n * h.M * 4));
+  CU(cudaMalloc(&r->labels, n * 4));
+  CU(cudaMalloc(&r->counter, 64));
+  CU(cudaMalloc(&r->totals, 64));
+  CU(cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking));
+  CU(cudaEventCreate(&r->ev[0]));
+  CU(cudaEventCreate(&r->ev[1]));
+  CU(cudaEventCreate(&r->ev[2]));
+  CU(cudaEventCreate(&r->ev[3]));
+  r->device_bytes = n * stride * FNB_CHUNK_BYTES + n * h.M * 4 + n * 4;
+  if (h.cur_nodes) {
+    CU(cudaMalloc(&d_blob, blob_bytes));
+    CU(cudaMemcpy(d_blob, blob, blob_bytes, cudaMemcpyHostToDevice));
+    const int threads = 256;
+    const int blocks = (int)std::min<uint64_t>((h.cur_nodes * 32 + threads - 1) / threads, (uint64_t)r->num_sms * 32);
+    deinterleave_kernel<<<blocks, threads>>>(d_blob, h.cur_nodes, h.node_size, (uint32_t)h.data_size, (uint32_t)h.M,
+                                             stride * FNB_CHUNK_BYTES, reinterpret_cast<unsigned char*>(r->vec),
+                                             r->adj, r->labels);
+    CU(cudaGetLastError());
+    CU(cudaMemset(r->counter, 0, 64));
+    validate_links_kernel<<<r->num_sms * 8, 256>>>(r->adj, h.cur_nodes * h.M, (uint32_t)h.cur_nodes, r->counter);
+    CU(cudaGetLastError());
+    unsigned int bad = 0;
+    CU(cudaMemcpy(&bad, r->counter, 4, cudaMemcpyDeviceToHost));
+    CU(cudaFree(d_blob));
+    if (bad) return fail(FNB_ERR_FORMAT, "%u links point outside [0, cur_num_nodes)", bad);
+  }
+  return FNB_OK;
+}
+
+static void free_replica(Replica* r) {
+  if (r->device < 0) return;
+  cudaSetDevice(r->device);
+  cudaFree(r->vec);
+  cudaFree(r->adj);
+  cudaFree(r->labels);
+  cudaFree(r->counter);
+  cudaFree(r->totals);
+  cudaFree(r->ws);
+  if (r->h_pinned) cudaFreeHost(r->h_pinned);
+  if (r->stream) cudaStreamDestroy(r->stream);
+  for (auto& e : r->ev)
+    if (e) cudaEventDestroy(e);
+}
+
+static int build_index(const unsigned char* file, size_t nbytes, int metric, int expect_dtype, const int* device_ids,
+                       int n_devices, fnb_index** out) {
+  if (!out) return fail(FNB_ERR_INVALID_ARG, "out is NULL");
+  *out = nullptr;
+  Header h;
+  int rc = parse_header(file, nbytes, metric, expect_dtype, &h);
+  if (rc != FNB_OK) return rc;
+  int ndev_avail = 0;
+  if (cudaGetDeviceCount(&ndev_avail) != cudaSuccess || ndev_avail == 0)
+    return fail(FNB_ERR_CUDA, "no CUDA device available; flatnav_b200 has no CPU path");
+  std::vector<int> devs;
+  if (device_ids == nullptr || n_devices <= 0) {
+    int cur = 0;
+    CU(cudaGetDevice(&cur));
+    devs.push_back(cur);
+  } else {
+    if (n_devices > 16) return fail(FNB_ERR_INVALID_ARG, "at most 16 replicas");
+    for (int i = 0; i < n_devices; i++) {
+      if (device_ids[i] < 0 || device_ids[i] >= ndev_avail)
+        return fail(FNB_ERR_INVALID_ARG, "device id %d out of range (have %d)", device_ids[i], ndev_avail);
+      devs.push_back(device_ids[i]);
+    }
+  }
+  int prev = 0;
+  cudaGetDevice(&prev);
+  fnb_index* ix = new fnb_index();
+  ix->h = h;
+  ix->nchunks = fnb_nchunks(h.data_size);
+  ix->stride = fnb_stride_chunks(ix->nchunks);
+  ix->G = fnb_lanes_per_row(ix->nchunks);
+  ix->replicas.resize(devs.size());
+  for (size_t i = 0; i < devs.size(); i++) {
+    rc = upload_replica(h, file + FNB_HEADER_BYTES, devs[i], &ix->replicas[i]);
+    if (rc != FNB_OK) {
+      std::string keep = g_last_error;
+      for (auto& r : ix->replicas) free_replica(&r);
+      delete ix;
+      cudaSetDevice(prev);
+      g_last_error = keep;
+      return rc;
+    }
+  }
+  cudaSetDevice(prev);
+  *out = ix;
+  return FNB_OK;
+}
+
+// ---- search dispatch ---------------------------------------------------------------------------------
+int plan_search(const fnb_index* ix, int64_t Q, int K, int ef, int ninit, SearchParams* p) {
+  if (Q < 0) return fail(FNB_ERR_INVALID_ARG, "negative query count");
+  if (K <= 0) return fail(FNB_ERR_INVALID_ARG, "K must be positive");
+  if (ninit <= 0) return fail(FNB_ERR_INVALID_ARG, "num_initializations must be greater than 0.");
+  if (Q >= (1ll << 31)) return fail(FNB_ERR_UNSUPPORTED, "more than 2^31 queries in one call");
+  const Header& h = ix->h;
+  memset(p, 0, sizeof(*p));
+  p->N = (uint32_t)h.cur_nodes;
+  p->M = (uint32_t)h.M;
+  p->dim = (uint32_t)h.dim;
+  p->nchunks = ix->nchunks;
+  p->stride = ix->stride;
+  p->Q = (uint32_t)Q;
+  p->K = (uint32_t)K;
+  p->B = (uint32_t)std::max(ef, K);  // Index.h:392
+  p->Bcap = (p->B + 31u) & ~31u;
+  // Index.h:851-852: step = cur_num_nodes / num_initializations (integer), at least 1
+  uint32_t step = (uint32_t)(h.cur_nodes / (uint64_t)ninit);
+  p->step = step ? step : 1;
+  p->nprobe = p->N ? (p->N + p->step - 1) / p->step : 0;
+  p->query_vec_ok = (h.data_size % FNB_CHUNK_BYTES) == 0 ? 1u : 0u;
+
+  // visited hash: ~20 distance evaluations per unit of ef on the BASELINE configs;
+  // aim for <= 50 % load without a reset, bounded by what lets >= 2 CTAs of 4 warps share an SM.
+  const char* env = getenv("FNB_HASH_BITS");
+  uint32_t bits = 10;
+  if (env && atoi(env) > 0) {
+    bits = (uint32_t)atoi(env);
+  } else {
+    const uint64_t want = (uint64_t)p->B * 40ull;
+    while ((1ull << bits) < want && bits < 13) bits++;
+  }
+  // the table must be able to hold the list plus one expansion with room to spare
+  while ((1ull << bits) * 3 / 4 < (uint64_t)p->Bcap + 64 && bits < 20) bits++;
+  p->hash_bits = bits;
+  p->hash_limit = (uint32_t)((1ull << bits) * 3 / 4);
+  p->warp_smem = p->Bcap * 8u + (1u << bits) * 4u + 128u;
+  if ((uint64_t)p->warp_smem * FNB_WARPS_PER_CTA > 227u * 1024u)
+    return fail(FNB_ERR_UNSUPPORTED, "ef_search=%d needs %u bytes of shared memory per query; limit is %u", ef,
+                p->warp_smem, 227u * 1024u / FNB_WARPS_PER_CTA);
+  return FNB_OK;
+}
+
+cudaError_t dispatch_search(const fnb_index* ix, const SearchParams& p, int num_sms, cudaStream_t s) {
+  switch (ix->h.data_type) {
+    case FNB_DTYPE_FLOAT32: return dispatch_search_f32(ix, p, num_sms, s);
+    case FNB_DTYPE_UINT8: return dispatch_search_u8(ix, p, num_sms, s);
+    default: return dispatch_search_i8(ix, p, num_sms, s);
+  }
+}
+
+static int ensure_workspace(Replica* r, size_t dev_bytes, size_t host_bytes) {
+  if (dev_bytes > r->ws_bytes) {
+    if (r->ws) CU(cudaFree(r->ws));
+    r->ws = nullptr;
+    r->ws_bytes = 0;
+    CU(cudaMalloc(&r->ws, dev_bytes));
+    r->ws_bytes = dev_bytes;
+  }
+  if (host_bytes > r->h_pinned_bytes) {
+    if (r->h_pinned) CU(cudaFreeHost(r->h_pinned));
+    r->h_pinned = nullptr;
+    r->h_pinned_bytes = 0;
+    CU(cudaMallocHost(&r->h_pinned, host_bytes));
+    r->h_pinned_bytes = host_bytes;
+  }
+  return FNB_OK;
+}
+
+static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+}  // namespace fnb
+
+using namespace fnb;
+
+// =====================================================================================================
+extern "C" {
+
+const char* fnb_last_error(void) { return g_last_error.c_str(); }
+const char* fnb_version(void) { return "flatnav_b200 0.1 (sm_100a)"; }
+
+int fnb_index_load(const char* path, int metric, int expect_dtype, const int* device_ids, int n_devices,
+                   fnb_index** out) {
+  if (!path) return fail(FNB_ERR_INVALID_ARG, "path is NULL");
+  FILE* f = fopen(path, "rb");
+  if (!f) return fail(FNB_ERR_IO, "Unable to open file for reading: %s", path);
+  fseek(f, 0, SEEK_END);
+  long long sz = ftell(f);
+  fseek(f, 0, SEEK_SET);
+  if (sz < 0) {
+    fclose(f);
+    return fail(FNB_ERR_IO, "cannot stat %s", path);
+  }
+  unsigned char* buf = (unsigned char*)malloc((size_t)sz ? (size_t)sz : 1);
+  if (!buf) {
+    fclose(f);
+    return fail(FNB_ERR_NOMEM, "cannot allocate %lld bytes to read %s", sz, path);
+  }
+  size_t got = fread(buf, 1, (size_t)sz, f);
+  fclose(f);
+  int rc = got == (size_t)sz ? build_index(buf, got, metric, expect_dtype, device_ids, n_devices, out)
+                             : fail(FNB_ERR_IO, "short read on %s", path);
+  free(buf);
+  return rc;
+}
+
+int fnb_index_from_memory(const void* file_bytes, size_t nbytes, int metric, int expect_dtype, const int* device_ids,
+                          int n_devices, fnb_index** out) {
+  if (!file_bytes) return fail(FNB_ERR_INVALID_ARG, "file_bytes is NULL");
+  return build_index((const unsigned char*)file_bytes, nbytes, metric, expect_dtype, device_ids, n_devices, out);
+}
+
+void fnb_index_free(fnb_index* ix) {
+  if (!ix) return;
+  int prev = 0;
+  cudaGetDevice(&prev);
+  for (auto& r : ix->replicas) free_replica(&r);
+  cudaSetDevice(prev);
+  delete ix;
+}
+
+int fnb_index_info(const fnb_index* ix, fnb_info* out) {
+  if (!ix || !out) return fail(FNB_ERR_INVALID_ARG, "NULL argument");
+  memset(out, 0, sizeof(*out));
+  out->data_type = ix->h.data_type;
+  out->metric = ix->h.metric;
+  out->max_edges_per_node = ix->h.M;
+  out->dim = ix->h.dim;
+  out->data_size_bytes = ix->h.data_size;
+  out->node_size_bytes = ix->h.node_size;
+  out->max_node_count = ix->h.max_nodes;
+  out->cur_num_nodes = ix->h.cur_nodes;
+  out->n_devices = (int32_t)ix->replicas.size();
+  for (size_t i = 0; i < ix->replicas.size() && i < 16; i++) out->device_ids[i] = ix->replicas[i].device;
+  out->device_bytes = ix->replicas.empty() ? 0 : ix->replicas[0].device_bytes;
+  out->row_stride_bytes = ix->stride * FNB_CHUNK_BYTES;
+  out->lanes_per_row = (uint32_t)ix->G;
+  return FNB_OK;
+}
+
+int fnb_index_save(const fnb_index* ix, const char* path) {
+  if (!ix || !path) return fail(FNB_ERR_INVALID_ARG, "NULL argument");
+  const Header& h = ix->h;
+  const Replica& r = ix->replicas[0];
+  int prev = 0;
+  cudaGetDevice(&prev);
+  CU(cudaSetDevice(r.device));
+  const uint64_t blob_bytes = h.node_size * h.max_nodes;
+  std::vector<unsigned char> host(FNB_HEADER_BYTES + blob_bytes, 0);
+  int32_t dt = h.data_type;
+  uint64_t v[7] = {h.M, h.data_size, h.node_size, h.max_nodes, h.cur_nodes, h.dim, h.data_size};
+  memcpy(host.data(), &dt, 4);
+  memcpy(host.data() + 4, v, 56);
+  if (h.cur_nodes) {
+    unsigned char* d_blob = nullptr;
+    CU(cudaMalloc(&d_blob, h.node_size * h.cur_nodes));
+    const int threads = 256;
+    const int blocks = (int)std::min<uint64_t>((h.cur_nodes * 32 + threads - 1) / threads, (uint64_t)r.num_sms * 32);
+    interleave_kernel<<<blocks, threads>>>(d_blob, h.cur_nodes, h.node_size, (uint32_t)h.data_size, (uint32_t)h.M,
+                                           ix->stride * FNB_CHUNK_BYTES, reinterpret_cast<const unsigned char*>(r.vec),
+                                           r.adj, r.labels);
+    CU(cudaGetLastError());
+    CU(cudaMemcpy(host.data() + FNB_HEADER_BYTES, d_blob, h.node_size * h.cur_nodes, cudaMemcpyDeviceToHost));
+    CU(cudaFree(d_blob));
+  }
+  cudaSetDevice(prev);
+  FILE* f = fopen(path, "wb");
+  if (!f) return fail(FNB_ERR_IO, "Unable to open file for writing: %s", path);
+  size_t put = fwrite(host.data(), 1, host.size(), f);
+  fclose(f);
+  if (put != host.size()) return fail(FNB_ERR_IO, "short write on %s", path);
+  return FNB_OK;
+}
+
+int fnb_search_device(fnb_index* ix, int replica, const void* d_queries, int64_t Q, int K, int ef_search,
+                      int num_initializations, float* d_out_dist, int32_t* d_out_label, uint32_t* d_ndist,
+                      uint32_t* d_nhops, void* cuda_stream) {
+  if (!ix) return fail(FNB_ERR_INVALID_ARG, "index is NULL");
+  if (replica < 0 || replica >= (int)ix->replicas.size()) return fail(FNB_ERR_INVALID_ARG, "bad replica %d", replica);
+  SearchParams p;
+  int rc = plan_search(ix, Q, K, ef_search, num_initializations, &p);
+  if (rc != FNB_OK) return rc;
+  if (Q == 0) return FNB_OK;
+  if (!d_queries || !d_out_dist || !d_out_label) return fail(FNB_ERR_INVALID_ARG, "NULL buffer");
+  Replica& r = ix->replicas[replica];
+  cudaStream_t s = (cudaStream_t)cuda_stream;
+  int prev = 0;
+  cudaGetDevice(&prev);
+  CU(cudaSetDevice(r.device));
+  p.vec = r.vec;
+  p.adj = r.adj;
+  p.labels = r.labels;
+  p.queries = d_queries;
+  p.out_dist = d_out_dist;
+  p.out_label = d_out_label;
+  p.out_ndist = d_ndist;
+  p.out_nhops = d_nhops;
+  p.counter = r.counter;
+  p.totals = r.totals;
+  CU(cudaMemsetAsync(r.counter, 0, 4, s));
+  CU(cudaMemsetAsync(r.totals, 0, 24, s));
+  cudaError_t e = dispatch_search(ix, p, r.num_sms, s);
+  cudaSetDevice(prev);
+  if (e != cudaSuccess) return fail(FNB_ERR_CUDA, "search kernel launch failed: %s", cudaGetErrorString(e));
+  return FNB_OK;
+}
+
+// Reads the totals written by the last fnb_search_device call on `replica` (after the caller synchronised).
+int fnb_search_device_totals(fnb_index* ix, int replica, int64_t* n_dist, int64_t* n_hops, int64_t* n_short) {
+  if (!ix || replica < 0 || replica >= (int)ix->replicas.size()) return fail(FNB_ERR_INVALID_ARG, "bad argument");
+  Replica& r = ix->replicas[replica];
+  int prev = 0;
+  cudaGetDevice(&prev);
+  CU(cudaSetDevice(r.device));
+  unsigned long long t[3];
+  CU(cudaMemcpy(t, r.totals, sizeof(t), cudaMemcpyDeviceToHost));
+  cudaSetDevice(prev);
+  if (n_dist) *n_dist = (int64_t)t[0];
+  if (n_hops) *n_hops = (int64_t)t[1];
+  if (n_short) *n_short = (int64_t)t[2];
+  return FNB_OK;
+}
+
+int fnb_search(fnb_index* ix, const void* queries, int64_t Q, int K, int ef_search, int num_initializations,
+               float* out_dist, int32_t* out_label, fnb_search_stats* stats) {
+  if (!ix) return fail(FNB_ERR_INVALID_ARG, "index is NULL");
+  SearchParams p0;
+  int rc = plan_search(ix, Q, K, ef_search, num_initializations, &p0);
+  if (rc != FNB_OK) return rc;
+  if (stats) memset(stats, 0, sizeof(*stats));
+  if (Q == 0) return FNB_OK;
+  if (!queries || !out_dist || !out_label) return fail(FNB_ERR_INVALID_ARG, "NULL buffer");
+  std::lock_guard<std::mutex> lock(ix->mu);
+  const Header& h = ix->h;
+  const int R = (int)ix->replicas.size();
+  int prev = 0;
+  cudaGetDevice(&prev);
+  const int64_t per = (Q + R - 1) / R;
+  struct Part {
+    int64_t q0, nq;
+    unsigned char *d_q, *d_dist, *d_label;
+  };
+  std::vector<Part> parts(R);
+  // enqueue everything on every replica first, then wait: replicas run concurrently from one host thread
+  for (int i = 0; i < R; i++) {
+    Replica& r = ix->replicas[i];
+    Part& pt = parts[i];
+    pt.q0 = std::min<int64_t>(Q, per * i);
+    pt.nq = std::min<int64_t>(Q, per * (i + 1)) - pt.q0;
+    if (pt.nq <= 0) continue;
+    CU(cudaSetDevice(r.device));
+    const size_t qb = (size_t)pt.nq * h.data_size, ob = (size_t)pt.nq * K * 4;
+    rc = ensure_workspace(&r, align256(qb) + 2 * align256(ob), 0);
+    if (rc != FNB_OK) {
+      cudaSetDevice(prev);
+      return rc;
+    }
+    pt.d_q = r.ws;
+    pt.d_dist = r.ws + align256(qb);
+    pt.d_label = pt.d_dist + align256(ob);
+    SearchParams p = p0;
+    p.Q = (uint32_t)pt.nq;
+    p.vec = r.vec;
+    p.adj = r.adj;
+    p.labels = r.labels;
+    p.queries = pt.d_q;
+    p.out_dist = reinterpret_cast<float*>(pt.d_dist);
+    p.out_label = reinterpret_cast<int32_t*>(pt.d_label);
+    p.counter = r.counter;
+    p.totals = r.totals;
+    CU(cudaEventRecord(r.ev[0], r.stream));
+    CU(cudaMemcpyAsync(pt.d_q, (const unsigned char*)queries + (size_t)pt.q0 * h.data_size, qb,
+                       cudaMemcpyHostToDevice, r.stream));
+    CU(cudaMemsetAsync(r.counter, 0, 4, r.stream));
+    CU(cudaMemsetAsync(r.totals, 0, 24, r.stream));
+    CU(cudaEventRecord(r.ev[1], r.stream));
+    cudaError_t e = dispatch_search(ix, p, r.num_sms, r.stream);
+    if (e != cudaSuccess) {
+      cudaSetDevice(prev);
+      return fail(FNB_ERR_CUDA, "search kernel launch failed: %s", cudaGetErrorString(e));
+    }
+    CU(cudaEventRecord(r.ev[2], r.stream));
+    CU(cudaMemcpyAsync(out_dist + (size_t)pt.q0 * K, pt.d_dist, ob, cudaMemcpyDeviceToHost, r.stream));
+    CU(cudaMemcpyAsync(out_label + (size_t)pt.q0 * K, pt.d_label, ob, cudaMemcpyDeviceToHost, r.stream));
+    CU(cudaEventRecord(r.ev[3], r.stream));
+  }
+  int64_t nd = 0, nh = 0, ns = 0;
+  float kms = 0.f, tms = 0.f;
+  int launches = 0;
+  for (int i = 0; i < R; i++) {
+    if (parts[i].nq <= 0) continue;
+    Replica& r = ix->replicas[i];
+    CU(cudaSetDevice(r.device));
+    CU(cudaStreamSynchronize(r.stream));
+    unsigned long long t[3];
+    CU(cudaMemcpy(t, r.totals, sizeof(t), cudaMemcpyDeviceToHost));
+    nd += (int64_t)t[0];
+    nh += (int64_t)t[1];
+    ns += (int64_t)t[2];
+    float a = 0.f, b = 0.f;
+    CU(cudaEventElapsedTime(&a, r.ev[1], r.ev[2]));
+    CU(cudaEventElapsedTime(&b, r.ev[0], r.ev[3]));
+    kms = std::max(kms, a);
+    tms = std::max(tms, b);
+    launches++;
+  }
+  cudaSetDevice(prev);
+  if (stats) {
+    stats->n_queries = Q;
+    stats->n_dist = nd;
+    stats->n_hops = nh;
+    stats->n_short = ns;
+    stats->algo_bytes = nd * (int64_t)h.data_size + nh * (int64_t)h.M * 4 + Q * (int64_t)h.data_size + Q * (int64_t)K * 8;
+    stats->kernel_ms = kms;
+    stats->total_ms = tms;
+    stats->kernel_launches = launches;
+  }
+  if (ns > 0) {
+    fail(FNB_SHORT_RESULT, "Search did not return the expected number of results for %lld of %lld queries.",
+         (long long)ns, (long long)Q);
+    return FNB_SHORT_RESULT;
+  }
+  return FNB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,235 @@
+"""`flatnav.index` of the reference, search side, on the B200 engine.
+
+Mirrors the classes `IndexL2Float / IndexL2Uint8 / IndexL2Int8 / IndexIPFloat / IndexIPUint8 / IndexIPInt8`
+bound in python-bindings/src/flatnav/bindings.cpp:358-395, 426-474 of the reference: same method names,
+argument meaning, return dtypes/shapes and exception types for `load_index`, `search`, `search_single`,
+`save`, `set_num_threads`, `num_threads`, `max_edges_per_node`, `get_query_distance_computations`.
+Construction-side methods (`add`, `allocate_nodes`, `build_graph_links`, `reorder`, `create`) are outside
+the hot path this package replaces: build the index with the reference and load it here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _capi
+from .data_type import DataType
+
+_NP = {DataType.float32: np.float32, DataType.uint8: np.uint8, DataType.int8: np.int8}
+_OUT_OF_SCOPE = ("index construction is outside the search hot path this package replaces; "
+                 "build the index with the reference flatnav and open it with load_index()")
+
+
+class _GpuIndex:
+    _metric: int = _capi.FNB_METRIC_L2
+    _data_type: DataType = DataType.float32
+
+    def __init__(self, handle: int):
+        self._h = C.c_void_p(handle)
+        info = _capi.FnbInfo()
+        _capi.check(_capi.lib().fnb_index_info(self._h, C.byref(info)))
+        self._info = info
+        self._dim = int(info.dim)
+        # Index::loadIndex sets _num_threads = max(1, hardware_concurrency / 2)  (Index.h:467)
+        self._num_threads = max(1, (os.cpu_count() or 1) // 2)
+        self._n_dist = 0
+        self.last_stats: dict = {}
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            try:
+                _capi.lib().fnb_index_free(h)
+            except Exception:
+                pass
+
+    # ---- loading / saving -------------------------------------------------------------------
+    @classmethod
+    def load_index(cls, filename: str, devices=None):
+        """Index<dist_t,label_t>::loadIndex (Index.h:442-479; bindings.cpp:303-306, :471).
+
+        `devices` (extension): CUDA device ids to replicate the index on; queries of a batch are then
+        split evenly across the replicas.  Default: the current device."""
+        out = C.c_void_p()
+        if devices:
+            arr = (C.c_int * len(devices))(*devices)
+            rc = _capi.lib().fnb_index_load(os.fsencode(filename), cls._metric, int(cls._data_type), arr, len(devices),
+                                            C.byref(out))
+        else:
+            rc = _capi.lib().fnb_index_load(os.fsencode(filename), cls._metric, int(cls._data_type), None, 0,
+                                            C.byref(out))
+        _capi.check(rc)
+        return cls(out.value)
+
+    @classmethod
+    def from_bytes(cls, blob, devices=None):
+        buf = np.frombuffer(blob, dtype=np.uint8)
+        out = C.c_void_p()
+        arr = (C.c_int * len(devices))(*devices) if devices else None
+        _capi.check(_capi.lib().fnb_index_from_memory(buf.ctypes.data, buf.size, cls._metric, int(cls._data_type), arr,
+                                                      len(devices) if devices else 0, C.byref(out)))
+        return cls(out.value)
+
+    def save(self, filename: str) -> None:
+        """Index::saveIndex (Index.h:481-490): writes the reference's cereal byte layout."""
+        _capi.check(_capi.lib().fnb_index_save(self._h, os.fsencode(filename)))
+
+    # ---- search -----------------------------------------------------------------------------
+    def _cast(self, a) -> np.ndarray:
+        # py::array_t<T, c_style | forcecast>  (bindings.cpp:36-51)
+        return np.ascontiguousarray(a, dtype=_NP[self._data_type])
+
+    def search(self, queries, K: int, ef_search: int, num_initializations: int = 100, *, out=None):
+        """PyIndex::search -> searchImpl (bindings.cpp:337-345, 161-228).
+
+        Returns (distances float32 [Q,K], labels int32 [Q,K]).  `out` (extension): a pair of preallocated
+        C-contiguous arrays of those shapes/dtypes (e.g. pinned memory) to write into instead of fresh ones."""
+        q = self._cast(queries)
+        if q.ndim != 2 or q.shape[1] != self._dim:
+            raise ValueError("Queries have incorrect dimensions.")
+        Q = q.shape[0]
+        if out is not None:
+            dist, lab = out
+            if (dist.shape != (Q, K) or lab.shape != (Q, K) or dist.dtype != np.float32 or lab.dtype != np.int32
+                    or not dist.flags.c_contiguous or not lab.flags.c_contiguous):
+                raise ValueError("out must be C-contiguous (float32[Q,K], int32[Q,K])")
+        else:
+            dist = np.empty((Q, K), dtype=np.float32)
+            lab = np.empty((Q, K), dtype=np.int32)
+        st = _capi.FnbSearchStats()
+        rc = _capi.lib().fnb_search(self._h, q.ctypes.data, Q, int(K), int(ef_search), int(num_initializations),
+                                    dist.ctypes.data, lab.ctypes.data, C.byref(st))
+        self.last_stats = st.as_dict()
+        self._n_dist += int(st.n_dist)
+        _capi.check(rc)
+        return dist, lab
+
+    def search_single(self, query, K: int, ef_search: int, num_initializations: int = 100):
+        """PyIndex::searchSingle -> searchSingleImpl (bindings.cpp:347-355, 121-159).
+
+        Returns (distances float32 [K], labels int32 [K])."""
+        q = self._cast(query)
+        if q.ndim != 1 or q.shape[0] != self._dim:
+            raise ValueError("Query has incorrect dimensions.")
+        d, l = self.search(q[None, :], K, ef_search, num_initializations)
+        return d[0], l[0]
+
+    def bruteforce(self, queries, K: int):
+        """Exact scan (extension; ground truth / exact re-rank). Returns (distances, labels) like search()."""
+        q = self._cast(queries)
+        if q.ndim != 2 or q.shape[1] != self._dim:
+            raise ValueError("Queries have incorrect dimensions.")
+        Q = q.shape[0]
+        dist = np.empty((Q, K), dtype=np.float32)
+        lab = np.empty((Q, K), dtype=np.int32)
+        _capi.check(_capi.lib().fnb_bruteforce(self._h, q.ctypes.data, Q, int(K), dist.ctypes.data, lab.ctypes.data))
+        return dist, lab
+
+    def search_device(self, d_queries: int, Q: int, K: int, ef_search: int, num_initializations: int, d_out_dist: int,
+                      d_out_label: int, stream: int = 0, d_ndist: int = 0, d_nhops: int = 0, replica: int = 0) -> None:
+        """Kernel-only path on device-resident buffers (raw device pointers as ints); asynchronous."""
+        _capi.check(_capi.lib().fnb_search_device(self._h, replica, d_queries, Q, K, ef_search, num_initializations,
+                                                  d_out_dist, d_out_label, d_ndist or None, d_nhops or None,
+                                                  stream or None))
+
+    def device_totals(self, replica: int = 0):
+        nd, nh, ns = C.c_int64(), C.c_int64(), C.c_int64()
+        _capi.check(_capi.lib().fnb_search_device_totals(self._h, replica, C.byref(nd), C.byref(nh), C.byref(ns)))
+        return nd.value, nh.value, ns.value
+
+    # ---- getters / knobs --------------------------------------------------------------------
+    def get_query_distance_computations(self) -> int:
+        """PyIndex::getQueryDistanceComputations (bindings.cpp:270-274): read-and-reset.
+
+        Counts database-row distance evaluations made by search() calls since the last read, including the
+        entry-selection probes (the reference adds `num_initializations` per search instead, Index.h:857-859,
+        and counts nothing at all on a loaded index because `collect_stats` is not serialised)."""
+        n, self._n_dist = self._n_dist, 0
+        return n
+
+    def set_num_threads(self, num_threads: int) -> None:
+        """Index::setNumThreads (Index.h:492-503). Kept for API parity; GPU execution ignores it."""
+        if num_threads <= 0 or num_threads > (os.cpu_count() or 1):
+            raise ValueError("Number of threads must be greater than 0 and less than or equal to "
+                             "the number of hardware threads.")
+        self._num_threads = int(num_threads)
+
+    @property
+    def num_threads(self) -> int:
+        return self._num_threads
+
+    @property
+    def max_edges_per_node(self) -> int:
+        return int(self._info.max_edges_per_node)
+
+    @property
+    def info(self) -> dict:
+        d = {k: getattr(self._info, k) for k, _ in self._info._fields_ if k != "device_ids"}
+        d["device_ids"] = list(self._info.device_ids)[: self._info.n_devices]
+        return d
+
+    # ---- construction side: out of scope ------------------------------------------------------
+    def add(self, *a, **k):
+        raise NotImplementedError(_OUT_OF_SCOPE)
+
+    def allocate_nodes(self, *a, **k):
+        raise NotImplementedError(_OUT_OF_SCOPE)
+
+    def build_graph_links(self, *a, **k):
+        raise NotImplementedError(_OUT_OF_SCOPE)
+
+    def reorder(self, *a, **k):
+        raise NotImplementedError(_OUT_OF_SCOPE)
+
+    def get_graph_outdegree_table(self, *a, **k):
+        raise NotImplementedError(_OUT_OF_SCOPE)
+
+
+class IndexL2Float(_GpuIndex):
+    _metric, _data_type = _capi.FNB_METRIC_L2, DataType.float32
+
+
+class IndexL2Uint8(_GpuIndex):
+    _metric, _data_type = _capi.FNB_METRIC_L2, DataType.uint8
+
+
+class IndexL2Int8(_GpuIndex):
+    _metric, _data_type = _capi.FNB_METRIC_L2, DataType.int8
+
+
+class IndexIPFloat(_GpuIndex):
+    _metric, _data_type = _capi.FNB_METRIC_IP, DataType.float32
+
+
+class IndexIPUint8(_GpuIndex):
+    _metric, _data_type = _capi.FNB_METRIC_IP, DataType.uint8
+
+
+class IndexIPInt8(_GpuIndex):
+    _metric, _data_type = _capi.FNB_METRIC_IP, DataType.int8
+
+
+_CLASSES = {
+    ("l2", DataType.float32): IndexL2Float, ("l2", DataType.uint8): IndexL2Uint8, ("l2", DataType.int8): IndexL2Int8,
+    ("angular", DataType.float32): IndexIPFloat, ("angular", DataType.uint8): IndexIPUint8,
+    ("angular", DataType.int8): IndexIPInt8,
+}
+
+
+def index_class(distance_type: str, index_data_type: DataType = DataType.float32):
+    """Class the reference's `create(distance_type, ..., index_data_type)` would instantiate (bindings.cpp:409-424)."""
+    dt = distance_type.lower()
+    if dt not in ("l2", "angular"):
+        raise ValueError("Invalid distance type: `" + dt + "` during index construction. Valid options "
+                         "include `l2` and `angular`.")  # validateDistanceType, bindings.cpp:397-407
+    return _CLASSES[(dt, DataType(index_data_type))]
+
+
+def create(distance_type: str, dim: int, dataset_size: int, max_edges_per_node: int,
+           index_data_type: DataType = DataType.float32, verbose: bool = False, collect_stats: bool = False):
+    """`flatnav.index.create` (bindings.cpp:484-504) builds an EMPTY index to `add()` into — construction,
+    which this package does not replace. The argument validation is kept; then it raises."""
+    index_class(distance_type, index_data_type)
+    raise NotImplementedError(_OUT_OF_SCOPE)

@@ -1,0 +1,136 @@
+/*
+ * flatnav_b200 — C ABI of the B200-native batched query engine for FlatNav's search hot path.
+ *
+ * The reference (BlaiseMuhirwa/flatnav) has no C ABI: its boundary for this path is the C++
+ * template `flatnav::Index<dist_t,label_t>` and the pybind11 class built on it.  This header is the
+ * thin, language-neutral layer placed beneath both surfaces; every entry point cites the reference
+ * interface it replaces (paths relative to the reference checkout).  The C++ shim
+ * (include/flatnav_b200/Index.h) and the Python package (flatnav_b200/) are written on top of it,
+ * and INTEGRATION.md shows the binding a reference maintainer would add.
+ *
+ * Conventions: every function returns FNB_OK (0), a positive informational status
+ * (FNB_SHORT_RESULT) or a negative error code, and never throws across the boundary;
+ * fnb_last_error() returns a thread-local message for the last non-zero status.  All pointers are
+ * plain host or device pointers owned by the caller unless stated otherwise; no torch types appear.
+ * There is no CPU fallback: without a CUDA device every compute entry point fails with
+ * FNB_ERR_CUDA.
+ */
+#ifndef FLATNAV_B200_H_
+#define FLATNAV_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* flatnav::util::DataType values that may appear in an index file (include/flatnav/util/Datatype.h:11-24);
+ * the enum value is part of the on-disk format (serialised as int32). */
+enum { FNB_DTYPE_UINT8 = 0, FNB_DTYPE_INT8 = 4, FNB_DTYPE_FLOAT32 = 9, FNB_DTYPE_ANY = -1 };
+
+/* flatnav::distances::MetricType (DistanceInterface.h).  The metric is NOT stored in the file — in the
+ * reference it is implied by the C++ class used to load (SquaredL2Distance / InnerProductDistance) — so
+ * the caller states it. */
+enum { FNB_METRIC_L2 = 0, FNB_METRIC_IP = 1 };
+
+enum {
+  FNB_OK = 0,
+  FNB_SHORT_RESULT = 1,      /* some query reached fewer than K nodes: slots hold label -1, distance +inf.
+                                (bindings.cpp:134-137,184-189 raise RuntimeError for this) */
+  FNB_ERR_INVALID_ARG = -1,  /* std::invalid_argument in the reference (e.g. num_initializations <= 0, Index.h:847) */
+  FNB_ERR_IO = -2,           /* std::runtime_error "Unable to open file" (Index.h:445-447, 484-486) */
+  FNB_ERR_FORMAT = -3,       /* header inconsistent / file truncated / dtype or metric mismatch */
+  FNB_ERR_CUDA = -4,         /* CUDA runtime failure or no device */
+  FNB_ERR_UNSUPPORTED = -5,  /* dimension / ef beyond what the kernels are instantiated for */
+  FNB_ERR_NOMEM = -6
+};
+
+typedef struct fnb_index fnb_index; /* opaque; owns device memory on every device it was loaded on */
+
+/* Mirrors the getters of Index<> (Index.h:517-531) plus what the loader decided. */
+typedef struct fnb_info {
+  int32_t data_type;          /* Index::getDataType */
+  int32_t metric;             /* FNB_METRIC_* as given at load time */
+  uint64_t max_edges_per_node; /* Index::maxEdgesPerNode (M) */
+  uint64_t dim;               /* Index::dataDimension */
+  uint64_t data_size_bytes;   /* Index::dataSizeBytes */
+  uint64_t node_size_bytes;   /* Index::nodeSizeBytes = data_size + 4 M + 4 */
+  uint64_t max_node_count;    /* Index::maxNodeCount */
+  uint64_t cur_num_nodes;     /* Index::currentNumNodes */
+  int32_t n_devices;          /* replicas (shard_mode 0) */
+  int32_t device_ids[16];
+  uint64_t device_bytes;      /* HBM bytes held per device */
+  uint32_t row_stride_bytes;  /* padded vector row pitch in HBM */
+  uint32_t lanes_per_row;     /* G of the distance kernel (csrc/fnb_layout.h) */
+} fnb_info;
+
+/* Counters of one fnb_search call (sums over the batch); feed the roofline accounting of bench.py. */
+typedef struct fnb_search_stats {
+  int64_t n_queries;
+  int64_t n_dist;        /* database-row distance evaluations incl. entry-selection probes */
+  int64_t n_hops;        /* expanded nodes */
+  int64_t n_short;       /* queries with fewer than K results */
+  int64_t algo_bytes;    /* n_dist*D*s + n_hops*M*4 + Q*D*s + Q*K*8    */
+  float kernel_ms;       /* device time of the traversal kernel(s), max over devices (CUDA events) */
+  float total_ms;        /* device time incl. host<->device copies (host-buffer entry point only) */
+  int32_t kernel_launches;
+  int32_t reserved;
+} fnb_search_stats;
+
+/* ---- load / save ----------------------------------------------------------------------------- */
+
+/* Replaces Index<dist_t,label_t>::loadIndex(filename) (include/flatnav/index/Index.h:442-479) and
+ * PyIndex::loadIndex (python-bindings/src/flatnav/bindings.cpp:303-306).  Parses the 60-byte cereal
+ * header + node blob, validates it, and lays the index out in HBM (vectors / links / labels as
+ * separate arrays) on each of `n_devices` devices (a full replica per device).
+ * expect_dtype: FNB_DTYPE_* or FNB_DTYPE_ANY.  device_ids may be NULL => {current device}. */
+int fnb_index_load(const char* path, int metric, int expect_dtype, const int* device_ids, int n_devices,
+                   fnb_index** out);
+
+/* Same, from an in-memory image of the file (header + blob). */
+int fnb_index_from_memory(const void* file_bytes, size_t nbytes, int metric, int expect_dtype, const int* device_ids,
+                          int n_devices, fnb_index** out);
+
+/* Replaces Index::saveIndex (Index.h:481-490): writes the reference's byte layout back (round trip). */
+int fnb_index_save(const fnb_index* index, const char* path);
+
+int fnb_index_info(const fnb_index* index, fnb_info* out);
+void fnb_index_free(fnb_index* index);
+
+/* ---- search ------------------------------------------------------------------------------------ */
+
+/* Replaces the batched fan-out PyIndex::searchImpl (bindings.cpp:161-228: executeInParallel over
+ * Index::search, Index.h:387-409) and, with Q == 1, Index::search / PyIndex::searchSingleImpl
+ * (bindings.cpp:121-159).  HOST buffers: `queries` is row-major [Q, dim] of the index data type,
+ * out_dist float32 [Q, K], out_label int32 [Q, K]; copies to/from the device happen inside.
+ * With several replicas the queries are split evenly across devices.
+ * Results per query: ascending distance, squared-L2 or 1 - <x,y> exactly as the reference returns them;
+ * labels are the node label field (Index.h:396-399).  stats may be NULL.  Thread-safe per index. */
+int fnb_search(fnb_index* index, const void* queries, int64_t Q, int K, int ef_search, int num_initializations,
+               float* out_dist, int32_t* out_label, fnb_search_stats* stats);
+
+/* Same traversal with DEVICE-resident buffers on replica `replica` (0-based), enqueued on `cuda_stream`
+ * (a cudaStream_t; NULL = legacy default stream) and not synchronised: the kernel-only path.
+ * d_ndist / d_nhops: optional per-query uint32 counters in device memory (may be NULL). */
+int fnb_search_device(fnb_index* index, int replica, const void* d_queries, int64_t Q, int K, int ef_search,
+                      int num_initializations, float* d_out_dist, int32_t* d_out_label, uint32_t* d_ndist,
+                      uint32_t* d_nhops, void* cuda_stream);
+
+/* Exact scan over all nodes (ground truth / exact re-rank).  The reference has no brute force of its own;
+ * semantics: top-K by (distance, node id), distances in the same arithmetic as fnb_search.  HOST buffers. */
+int fnb_bruteforce(fnb_index* index, const void* queries, int64_t Q, int K, float* out_dist, int32_t* out_label);
+
+/* Dataset-sharded search: k-way merge of `n_lists` per-shard result lists (each [Q, K], ascending) that
+ * were gathered into DEVICE buffers d_dist / d_label of shape [n_lists, Q, K]; writes the global top-K
+ * ([Q, K], ties -> lower label) to d_out_*.  Enqueued on cuda_stream. */
+int fnb_merge_topk(const float* d_dist, const int32_t* d_label, int n_lists, int64_t Q, int K, float* d_out_dist,
+                   int32_t* d_out_label, void* cuda_stream);
+
+const char* fnb_last_error(void);
+const char* fnb_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FLATNAV_B200_H_ */

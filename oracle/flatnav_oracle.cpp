@@ -294,24 +294,29 @@ void search_list(const ora_index& ix, const Dist& dist, const void* q, int K, in
     if (pick == L.size()) break;  // every entry of the list is expanded
     L[pick].expanded = true;
     c.nhops++;
-    bool full = L.size() >= B;
-    float worst = L.back().d;
     const uint32_t* links = node_links(ix, L[pick].id);
-    fresh.clear();
-    for (uint64_t i = 0; i < ix.M; i++) {
-      uint32_t nb = links[i];
-      if (visited[nb]) continue;
-      visited[nb] = 1;
-      float d = dist(q, node_data(ix, nb));
-      c.ndist++;
-      if (!full || d < worst) fresh.push_back({d, nb, false});
+    // Links are taken in groups of 32 (one warp-wide load in the CUDA kernel): acceptance is tested against
+    // the list as it stood before the group, then the group's accepted entries are merged at once.  For
+    // M <= 32 this is one batch per expansion; it differs from link-by-link processing only on exact ties.
+    for (uint64_t l0 = 0; l0 < ix.M; l0 += 32) {
+      bool full = L.size() >= B;
+      float worst = L.back().d;
+      fresh.clear();
+      for (uint64_t i = l0; i < ix.M && i < l0 + 32; i++) {
+        uint32_t nb = links[i];
+        if (visited[nb]) continue;
+        visited[nb] = 1;
+        float d = dist(q, node_data(ix, nb));
+        c.ndist++;
+        if (!full || d < worst) fresh.push_back({d, nb, false});
+      }
+      if (fresh.empty()) continue;
+      std::sort(fresh.begin(), fresh.end(), key_less);
+      std::vector<Entry> merged(L.size() + fresh.size());
+      std::merge(L.begin(), L.end(), fresh.begin(), fresh.end(), merged.begin(), key_less);
+      if (merged.size() > B) merged.resize(B);
+      L.swap(merged);
     }
-    if (fresh.empty()) continue;
-    std::sort(fresh.begin(), fresh.end(), key_less);
-    std::vector<Entry> merged(L.size() + fresh.size());
-    std::merge(L.begin(), L.end(), fresh.begin(), fresh.end(), merged.begin(), key_less);
-    if (merged.size() > B) merged.resize(B);
-    L.swap(merged);
   }
   out.clear();
   for (size_t i = 0; i < L.size() && i < (size_t)K; i++) out.emplace_back(L[i].d, node_label(ix, L[i].id));

@@ -1,0 +1,90 @@
+"""CPU: the C-ABI library loads, exports every symbol include/flatnav_b200.h declares, and the host-side
+mirror of the reference's Python interface has the reference's names / validation / errors.  No compute."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+import flatnav_b200
+from conftest import ROOT, golden_index_path
+from flatnav_b200 import _capi
+from flatnav_b200.data_type import DataType
+
+
+def declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "flatnav_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(fnb_[a-z_0-9]+)\s*\(", hdr)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _capi.lib()
+    syms = declared_symbols()
+    assert len(syms) >= 11
+    for s in syms:
+        assert hasattr(lib, s), s
+    assert set(syms) <= set(_capi.EXPORTS) | {"fnb_search_device_totals"}
+    assert b"sm_100a" in lib.fnb_version()
+
+
+def test_namespace_mirrors_reference():
+    # python-bindings/src/flatnav/__init__.py:9-27 and bindings.cpp:358-395, 507-521
+    for name in ("IndexL2Float", "IndexIPFloat", "IndexL2Uint8", "IndexIPUint8", "IndexL2Int8", "IndexIPInt8", "create"):
+        assert hasattr(flatnav_b200.index, name)
+    assert int(DataType.float32) == 9 and int(DataType.int8) == 4 and int(DataType.uint8) == 0
+    assert flatnav_b200.MetricType.L2 == 0 and flatnav_b200.MetricType.IP == 1
+    for m in ("search", "search_single", "load_index", "save", "set_num_threads", "get_query_distance_computations",
+              "add", "allocate_nodes", "reorder", "build_graph_links", "get_graph_outdegree_table"):
+        assert hasattr(flatnav_b200.index.IndexL2Float, m)
+
+
+def test_create_validates_distance_type_like_reference():
+    with pytest.raises(ValueError, match="Invalid distance type"):  # bindings.cpp:397-407
+        flatnav_b200.index.create("cosine", 8, 10, 4)
+    with pytest.raises(NotImplementedError):
+        flatnav_b200.index.create("l2", 8, 10, 4)
+    assert flatnav_b200.index.index_class("angular", DataType.uint8) is flatnav_b200.index.IndexIPUint8
+    assert flatnav_b200.index.index_class("L2") is flatnav_b200.index.IndexL2Float
+
+
+def test_load_missing_file_is_runtime_error():
+    with pytest.raises(RuntimeError, match="Unable to open file for reading"):  # Index.h:445-447
+        flatnav_b200.index.IndexL2Float.load_index("/nonexistent/file.idx")
+
+
+def test_header_validation_happens_before_any_device_work(tmp_path):
+    raw = bytearray(open(golden_index_path("l2_f32_d7"), "rb").read())
+    # wrong dtype requested for the class
+    with pytest.raises(RuntimeError, match="data_type"):
+        flatnav_b200.index.IndexL2Uint8.from_bytes(bytes(raw))
+    bad = bytearray(raw)
+    bad[20:28] = (12345).to_bytes(8, "little")  # node_size != data_size + 4M + 4
+    with pytest.raises(RuntimeError, match="node_size"):
+        flatnav_b200.index.IndexL2Float.from_bytes(bytes(bad))
+    with pytest.raises(RuntimeError, match="truncated"):
+        flatnav_b200.index.IndexL2Float.from_bytes(bytes(raw[:1000]))
+    with pytest.raises(RuntimeError, match="60-byte"):
+        flatnav_b200.index.IndexL2Float.from_bytes(bytes(raw[:10]))
+
+
+def test_no_cpu_fallback_without_device():
+    import ctypes as C
+    n = C.c_int(0)
+    try:
+        cudart = C.CDLL("libcudart.so.12")
+        have = cudart.cudaGetDeviceCount(C.byref(n)) == 0 and n.value > 0
+    except OSError:
+        have = False
+    if have:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(RuntimeError, match="no CUDA device"):
+        flatnav_b200.index.IndexL2Float.load_index(golden_index_path("l2_f32_d7"))
+
+
+def test_product_never_imports_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "flatnav_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src and "liboracle" not in src, f

@@ -1,0 +1,44 @@
+"""Benchmark / test infrastructure (NOT part of the product package): materialise a synthetic dataset and an
+index file for it.  Index CONSTRUCTION is outside the hot path flatnav_b200 replaces (component
+#10), so the graph is built by the unmodified reference (oracle/_ref/ref_flatnav_*: Index::addBatch +
+saveIndex) and cached under data_cache/ keyed by every parameter that shapes it."""
+from __future__ import annotations
+
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+CACHE = os.environ.get("FNB_DATA_CACHE", os.path.join(ROOT, "data_cache"))
+
+
+def index_name(gen: str, n: int, dim: int, metric: str, M: int, efc: int) -> str:
+    return f"{gen}_n{n}_d{dim}_{metric}_M{M}_efc{efc}_seed42"
+
+
+def ensure_index(gen: str, n: int, dim: int, metric: str, M: int = 32, efc: int = 100, threads: int = 0):
+    """Return (path, info).  Builds with the reference binary if the file is not cached."""
+    from flatnav_b200 import synthetic
+    from oracle import refbin
+    os.makedirs(CACHE, exist_ok=True)
+    path = os.path.join(CACHE, index_name(gen, n, dim, metric, M, efc) + ".idx")
+    meta = path + ".json"
+    if os.path.exists(path) and os.path.exists(meta):
+        info = json.load(open(meta))
+        info["cached"] = True
+        return path, info
+    if not refbin.available():
+        raise RuntimeError("no cached index and the reference builder (oracle/_ref) cannot run on this host")
+    t0 = time.time()
+    data = synthetic.make(gen, n, dim)
+    t_gen = time.time() - t0
+    info = refbin.build_index(data, metric, M, efc, path + ".tmp", threads=threads or (os.cpu_count() or 1))
+    os.replace(path + ".tmp", path)
+    info = {"build_seconds": info["seconds"], "build_threads": info["threads"], "gen_seconds": round(t_gen, 2),
+            "builder": "reference " + refbin.isa(), "cached": False}
+    json.dump(info, open(meta, "w"))
+    return path, info
