@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libflatnav_b200.so")
+LIB_PATH = os.environ.get("FNB_LIB_PATH") or os.path.join(HERE, "libflatnav_b200.so")  # env: development A/B builds
 
 FNB_OK, FNB_SHORT_RESULT = 0, 1
 FNB_ERR_INVALID_ARG, FNB_ERR_IO, FNB_ERR_FORMAT, FNB_ERR_CUDA, FNB_ERR_UNSUPPORTED, FNB_ERR_NOMEM = -1, -2, -3, -4, -5, -6

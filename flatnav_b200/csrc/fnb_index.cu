@@ -262,21 +262,11 @@ int plan_search(const fnb_index* ix, int64_t Q, int K, int ef, int ninit, Search
   p->nprobe = p->N ? (p->N + p->step - 1) / p->step : 0;
   p->query_vec_ok = (h.data_size % FNB_CHUNK_BYTES) == 0 ? 1u : 0u;
 
-  // visited hash: ~20 distance evaluations per unit of ef on the BASELINE configs;
-  // aim for <= 50 % load without a reset, bounded by what lets >= 2 CTAs of 4 warps share an SM.
-  const char* env = getenv("FNB_HASH_BITS");
-  uint32_t bits = 10;
-  if (env && atoi(env) > 0) {
-    bits = (uint32_t)atoi(env);
-  } else {
-    const uint64_t want = (uint64_t)p->B * 40ull;
-    while ((1ull << bits) < want && bits < 13) bits++;
-  }
-  // the table must be able to hold the list plus one expansion with room to spare
-  while ((1ull << bits) * 3 / 4 < (uint64_t)p->Bcap + 64 && bits < 20) bits++;
-  p->hash_bits = bits;
-  p->hash_limit = (uint32_t)((1ull << bits) * 3 / 4);
-  p->warp_smem = p->Bcap * 8u + (1u << bits) * 4u + 128u;
+  p->Bpow2 = 1;
+  while (p->Bpow2 * 2u <= p->Bcap) p->Bpow2 *= 2u;
+  p->lines_per_row = (ix->stride * FNB_CHUNK_BYTES + 127u) / 128u;
+  const char* env = getenv("FNB_VS_BUCKETS");  // development / test knob: visited-set buckets per query
+  size_visited(*p, env ? atoi(env) : 0, fnb_min_ctas(fnb_chunks_per_lane(ix->nchunks)));
   if ((uint64_t)p->warp_smem * FNB_WARPS_PER_CTA > 227u * 1024u)
     return fail(FNB_ERR_UNSUPPORTED, "ef_search=%d needs %u bytes of shared memory per query; limit is %u", ef,
                 p->warp_smem, 227u * 1024u / FNB_WARPS_PER_CTA);

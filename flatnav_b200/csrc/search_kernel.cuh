@@ -4,8 +4,8 @@
 //   Index::search / initializeSearch / beamSearch / processCandidateNode
 //       (include/flatnav/index/Index.h:387-409, 845-870, 606-659, 661-707 of the reference)
 //   the two std::priority_queue heaps (Index.h:47-53, 623-624)  -> one sorted list in shared memory
-//   VisitedSet / VisitedSetPool (util/VisitedSetPool.h:16-197)   -> per-warp open-addressing hash in
-//                                                                  shared memory with a bounded reset
+//   VisitedSet / VisitedSetPool (util/VisitedSetPool.h:16-197)   -> per-warp bucketed tag set in shared
+//                                                                  memory (never a false positive, may forget)
 //   the AVX-512/AVX/SSE distance kernels (util/SquaredL2SimdExtensions.h, InnerProductSimdExtensions.h)
 //                                                                -> 128-bit gathers + shuffle reduction
 //   executeInParallel (util/Multithreading.h:18-48)              -> persistent warps pulling query ids
@@ -39,6 +39,16 @@ enum { DT_F32 = 0, DT_U8 = 1, DT_I8 = 2 };
 enum { M_L2 = 0, M_IP = 1 };
 
 #define FNB_WARPS_PER_CTA 4
+// Occupancy plan.  The traversal is latency-bound per warp (a hop is a chain of dependent steps), so throughput
+// comes from resident warps: 24 per SM for rows up to 512 B.  Registers are kept low by holding only ONE
+// warp-wide batch of row loads in registers (CH loads per lane) — every further fresh row of the expansion is
+// already on its way into L2 via prefetch.global.L2, which costs no registers.  Longer rows need more registers
+// per lane (query + one batch), so fewer CTAs are planned for them.
+#ifndef FNB_CTAS_SHORT_ROWS
+#define FNB_CTAS_SHORT_ROWS 6
+#endif
+__host__ __device__ constexpr int fnb_min_ctas(int ch) { return ch <= 4 ? FNB_CTAS_SHORT_ROWS : (ch <= 8 ? 4 : 3); }
+__host__ __device__ constexpr int fnb_batches_in_flight(int ch) { return ch >= 4 ? 1 : 4 / ch; }
 #define FNB_FULL 0xffffffffu
 #define FNB_EMPTY 0xffffffffu
 
@@ -54,9 +64,13 @@ struct SearchParams {
   unsigned int* counter;               // persistent-warp work counter (zeroed before launch)
   unsigned long long* totals;          // [3]: sum n_dist, sum n_hops, #short results
   uint32_t N, M, dim, nchunks, stride;
-  uint32_t Q, K, B, Bcap;
+  uint32_t Q, K, B, Bcap, Bpow2;  // Bpow2: largest power of two <= Bcap (fixed-step lower_bound)
   uint32_t nprobe, step;
-  uint32_t hash_bits, hash_limit;
+  uint32_t vs_buckets;   // visited set: number of 16-byte buckets per warp
+  uint32_t vs_shift;     // 32 - nbits, nbits = ceil(log2(N)): ids are hashed by a bijection of [0, 2^nbits)
+  uint32_t vs_tag_mask;  // low bits of the hash kept as the tag (unique within a bucket)
+  uint32_t vs_wide;      // 1 => 4 x 32-bit tags per bucket (huge N), 0 => 8 x 16-bit tags
+  uint32_t lines_per_row;  // 128-byte lines per padded row (for the L2 prefetch)
   uint32_t warp_smem;  // bytes of shared memory per warp
   uint32_t query_vec_ok;  // 1 => query rows are 16-byte aligned and a whole number of chunks
 };
@@ -67,6 +81,17 @@ __device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
   asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
                : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
                : "l"(p));
+  return r;
+}
+// predicated form: when `pred` is false nothing is loaded and the destination keeps garbage that the
+// caller never uses (saves the zero-fill moves a C++ `if` would need)
+__device__ __forceinline__ uint4 ldg_stream_if(const uint4* p, bool pred) {
+  uint4 r;
+  asm volatile(
+      "{\n\t.reg .pred pp;\n\tsetp.ne.b32 pp, %5, 0;\n\t"
+      "@pp ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];\n\t}"
+      : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+      : "l"(p), "r"((int)pred));
   return r;
 }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
@@ -198,34 +223,47 @@ __device__ __forceinline__ uint4 load_query_chunk(const SearchParams& p, uint32_
 
 // ---- distances of up to 32 rows (one id per lane), cooperatively ------------------------------------
 // Each valid lane gets back the distance of ITS row.  s_ids: 32-entry per-warp scratch.
-template <int DT, int METRIC, int G, int CH>
+// EXACT: the row is exactly G*CH chunks (e.g. D=128 f32 with G=8, CH=4): no per-chunk bounds test.
+// prefetch: rows beyond the first register batch are pulled into L2 right away (prefetch.global.L2 costs no
+// registers), so the later register batches pay an L2 hit instead of another HBM round trip each.
+template <int DT, int METRIC, int G, int CH, bool EXACT>
 __device__ __forceinline__ float batch_distance(const SearchParams& p, const uint4 (&q)[CH], uint32_t my_id,
-                                                bool valid, uint32_t* s_ids, int lane) {
+                                                bool valid, uint32_t* s_ids, int lane, bool prefetch) {
   typedef Arith<DT, METRIC> A;
   constexpr int RPI = 32 / G;                                   // rows per warp-wide load instruction
-  constexpr int U = (20 / CH) < 1 ? 1 : ((20 / CH) > 8 ? 8 : (20 / CH));  // load instructions in flight / CH
+  constexpr int U = fnb_batches_in_flight(CH);  // warp-wide load batches held in registers
   const unsigned mask = __ballot_sync(FNB_FULL, valid);
   const int n = __popc(mask);
   const int myrank = __popc(mask & ((1u << lane) - 1u));
   if (valid) s_ids[myrank] = my_id;
   __syncwarp();
   const int g = lane / G, pos = lane % G;
+  if (prefetch && n > RPI * U) {
+    for (int c0 = RPI * U; c0 < n; c0 += RPI) {
+      const int c = c0 + g;
+      if (c < n) {
+        const uint4* row = p.vec + (size_t)s_ids[c] * p.stride;
+        for (uint32_t line = (uint32_t)pos; line < p.lines_per_row; line += G) prefetch_l2(row + line * 8u);
+      }
+    }
+  }
   float mine = 0.f;
   for (int r0 = 0; r0 < n; r0 += RPI * U) {
     uint4 x[U][CH];
 #pragma unroll
     for (int u = 0; u < U; u++) {
-      const int c = r0 + u * RPI + g;
-      const bool ok = c < n;
-      const uint32_t rid = s_ids[ok ? c : 0];
-      const uint4* row = p.vec + (size_t)rid * p.stride;
+      if (r0 + u * RPI < n) {  // warp-uniform
+        const int c = r0 + u * RPI + g;
+        const bool ok = c < n;
+        const uint32_t rid = s_ids[ok ? c : 0];
+        const uint4* row = p.vec + (size_t)rid * p.stride + pos;
 #pragma unroll
-      for (int k = 0; k < CH; k++) {
-        const uint32_t chunk = (uint32_t)(k * G + pos);
-        if (ok && chunk < p.nchunks)
-          x[u][k] = ldg_stream(row + chunk);
-        else
-          x[u][k] = make_uint4(0, 0, 0, 0);
+        for (int k = 0; k < CH; k++) {
+          if (EXACT)
+            x[u][k] = ldg_stream_if(row + k * G, ok);
+          else
+            x[u][k] = ldg_stream_if(row + k * G, ok && (uint32_t)(k * G + pos) < p.nchunks);
+        }
       }
     }
 #pragma unroll
@@ -233,14 +271,15 @@ __device__ __forceinline__ float batch_distance(const SearchParams& p, const uin
       if (r0 + u * RPI < n) {  // warp-uniform
         typename A::acc_t acc = 0;
 #pragma unroll
-        for (int k = 0; k < CH; k++) A::step(acc, q[k], x[u][k]);
+        for (int k = 0; k < CH; k++) {
+          if (EXACT || (uint32_t)(k * G + pos) < p.nchunks) A::step(acc, q[k], x[u][k]);
+        }
 #pragma unroll
         for (int off = G / 2; off > 0; off >>= 1) acc = A::combine(acc, shfl_xor_t(acc, off));
         const float d = A::finish(acc);
-        const int cbase = r0 + u * RPI;
-        const int rel = myrank - cbase;  // which group of this instruction handled my row (if 0 <= rel < RPI)
+        const int rel = myrank - (r0 + u * RPI);  // which group of this instruction handled my row
         const float v = __shfl_sync(FNB_FULL, d, (rel * G) & 31);
-        if (valid && rel >= 0 && rel < RPI) mine = v;
+        if (rel >= 0 && rel < RPI) mine = v;
       }
     }
   }
@@ -248,39 +287,138 @@ __device__ __forceinline__ float batch_distance(const SearchParams& p, const uin
   return mine;
 }
 
-// ---- visited hash ----------------------------------------------------------------------------------
-__device__ __forceinline__ bool hash_test_and_set(uint32_t* tab, uint32_t bits, uint32_t id) {
-  const uint32_t cap_mask = (1u << bits) - 1u;
-  uint32_t slot = (id * 0x9E3779B1u) >> (32 - bits);
-  for (;;) {
-    uint32_t v = reinterpret_cast<volatile uint32_t*>(tab)[slot];
-    if (v == id) return false;
-    if (v == FNB_EMPTY) {
-      uint32_t old = atomicCAS(&tab[slot], FNB_EMPTY, id);
-      if (old == FNB_EMPTY) return true;
-      if (old == id) return false;
-    }
-    slot = (slot + 1) & cap_mask;
+// ---- visited set ------------------------------------------------------------------------------------
+// Replaces VisitedSet (util/VisitedSetPool.h:16-89: an N-byte table per thread).  Per warp, in shared memory:
+// `vs_buckets` buckets of 16 bytes, each holding 8 16-bit tags (or 4 32-bit tags when N is so large that a tag
+// does not fit 15 bits).  A node id is mapped by a bijection h of [0, 2^nbits) (odd multiplier), the bucket is
+// floor(h * buckets / 2^nbits) and the tag is the low bits of h, chosen wide enough that (bucket, tag)
+// identifies the id exactly: the set can never report an unvisited node as visited.  It CAN forget (a full
+// bucket overwrites a slot; two lanes racing for one empty slot lose one insert).  Forgetting is harmless for the
+// result: a forgotten node that is met again is re-evaluated and either rejected again (its distance is >= the
+// current worst, which only decreases) or, if it still sits in the list, dropped by the duplicate test of the
+// merge.  It only costs the extra row fetch; at the default sizing (>= 2 slots per expected visit) the measured
+// re-evaluation rate is below 1 %.  One 128-bit load, straight-line code, no atomics, no probing loop.
+__device__ __forceinline__ bool visited_test_and_set(uint32_t* tab, const SearchParams& p, uint32_t id) {
+  const uint32_t h = (id * 0x9E3779B1u) << p.vs_shift;  // bijective hash, left-aligned
+  const uint32_t bucket = __umulhi(h, p.vs_buckets);
+  const uint32_t tag = (h >> p.vs_shift) & p.vs_tag_mask;
+  uint4* bp = reinterpret_cast<uint4*>(tab) + bucket;
+  uint4 w;  // one 128-bit shared-memory load, never cached in registers across calls
+  asm volatile("ld.volatile.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w)
+               : "r"((uint32_t)__cvta_generic_to_shared(bp)));
+  if (!p.vs_wide) {
+    const uint32_t t2 = tag | (tag << 16);
+    // halfword-equals test: zero halfword of (w ^ t2)
+    uint32_t x, hit = 0, e0, e1, e2, e3;
+    x = w.x ^ t2; hit |= (x - 0x00010001u) & ~x;
+    x = w.y ^ t2; hit |= (x - 0x00010001u) & ~x;
+    x = w.z ^ t2; hit |= (x - 0x00010001u) & ~x;
+    x = w.w ^ t2; hit |= (x - 0x00010001u) & ~x;
+    if (hit & 0x80008000u) return false;
+    // first empty (0xFFFF) halfword, else a victim chosen by the hash
+    x = ~w.x; e0 = (x - 0x00010001u) & ~x & 0x80008000u;
+    x = ~w.y; e1 = (x - 0x00010001u) & ~x & 0x80008000u;
+    x = ~w.z; e2 = (x - 0x00010001u) & ~x & 0x80008000u;
+    x = ~w.w; e3 = (x - 0x00010001u) & ~x & 0x80008000u;
+    uint32_t slot;
+    if (e0) slot = (e0 & 0x8000u) ? 0u : 1u;
+    else if (e1) slot = (e1 & 0x8000u) ? 2u : 3u;
+    else if (e2) slot = (e2 & 0x8000u) ? 4u : 5u;
+    else if (e3) slot = (e3 & 0x8000u) ? 6u : 7u;
+    else slot = (h >> 13) & 7u;
+    reinterpret_cast<volatile uint16_t*>(bp)[slot] = (uint16_t)tag;
+    return true;
+  } else {
+    if (w.x == tag || w.y == tag || w.z == tag || w.w == tag) return false;
+    uint32_t slot;
+    if (w.x == FNB_EMPTY) slot = 0;
+    else if (w.y == FNB_EMPTY) slot = 1;
+    else if (w.z == FNB_EMPTY) slot = 2;
+    else if (w.w == FNB_EMPTY) slot = 3;
+    else slot = (h >> 13) & 3u;
+    reinterpret_cast<volatile uint32_t*>(bp)[slot] = tag;
+    return true;
   }
 }
 
-__device__ __forceinline__ void hash_clear(uint32_t* tab, uint32_t bits, int lane) {
+__device__ __forceinline__ void visited_clear(uint32_t* tab, uint32_t buckets, int lane) {
   uint4* t4 = reinterpret_cast<uint4*>(tab);
-  const uint32_t n4 = (1u << bits) / 4;
   const uint4 e = make_uint4(FNB_EMPTY, FNB_EMPTY, FNB_EMPTY, FNB_EMPTY);
-  for (uint32_t i = lane; i < n4; i += 32) t4[i] = e;
+  for (uint32_t i = lane; i < buckets; i += 32) t4[i] = e;
 }
 
 // ---------------------------------------------------------------------------------------------------
-template <int DT, int METRIC, int G, int CH>
-__global__ void __launch_bounds__(FNB_WARPS_PER_CTA * 32, 3) fnb_search_kernel(const SearchParams p) {
+// Merge of the accepted entries of one expansion into the sorted list (in place, shared memory).
+//   key/acc : this lane's candidate (valid iff acc)
+// Every lane runs the same fixed-step lower_bound (no divergent loop).  A candidate whose (distance, id) is
+// already in the list (a node the visited set forgot) or that equals another lane's candidate (a link listed
+// twice) is dropped.  Each remaining lane's final slot is fin = lower_bound + rank among the accepted.  The
+// final slots of the new entries form a bitmask T over [0, len + n_acc); old entries keep their order and fill
+// the other slots, so destination t takes old entry t - popc(T[0..t)).  Chunks of 32 destinations are rewritten
+// from the top down, which makes the in-place update safe (a source is never above its destination).
+__device__ __forceinline__ void merge_accepted(volatile uint64_t* list, uint32_t& len, uint32_t& start,
+                                               const uint32_t B, const uint32_t Bpow2, const uint64_t key, bool acc,
+                                               const int lane) {
+  // lower_bound(list[0..len), key) ignoring the expanded bit
+  uint32_t lo = 0;
+  for (uint32_t step = Bpow2; step; step >>= 1) {
+    const uint32_t idx = lo + step;
+    if (idx <= len && (list[idx - 1] & ~1ull) < key) lo = idx;
+  }
+  if (lo < len && (list[lo] & ~1ull) == key) acc = false;  // already in the list
+  unsigned am = __ballot_sync(FNB_FULL, acc);
+  uint32_t rank = 0;
+  bool dup = false;
+  for (unsigned m = am; m; m &= m - 1) {
+    const int s = __ffs(m) - 1;
+    const uint64_t kj = shfl64(key, s);
+    rank += (kj < key) ? 1u : 0u;
+    dup |= (kj == key) && (s < lane);
+  }
+  if (__any_sync(FNB_FULL, acc && dup)) {  // a link listed twice: keep the lowest lane, redo the ranks
+    acc = acc && !dup;
+    am = __ballot_sync(FNB_FULL, acc);
+    rank = 0;
+    for (unsigned m = am; m; m &= m - 1) rank += (shfl64(key, __ffs(m) - 1) < key) ? 1u : 0u;
+  }
+  if (!am) return;
+  const uint32_t n_acc = (uint32_t)__popc(am);
+  const uint32_t fin = acc ? lo + rank : 0xffffffffu;
+  const uint32_t fin_min = __reduce_min_sync(FNB_FULL, fin);
+  const uint32_t new_len = min(B, len + n_acc);
+  if (fin_min < new_len) {
+    const int c_lo = (int)(fin_min >> 5), c_hi = (int)((new_len - 1) >> 5);
+    uint32_t below = (uint32_t)__popc(__ballot_sync(FNB_FULL, acc && (fin >> 5) < (uint32_t)c_hi));
+    for (int c = c_hi; c >= c_lo; c--) {
+      const uint32_t T = __reduce_or_sync(FNB_FULL, (acc && (fin >> 5) == (uint32_t)c) ? (1u << (fin & 31)) : 0u);
+      const uint32_t t = (uint32_t)c * 32 + lane;
+      const bool is_new = (T >> lane) & 1u;
+      const uint32_t src = t - below - (uint32_t)__popc(T & ((1u << lane) - 1u));
+      const bool mv = t < new_len && !is_new && src != t;
+      const uint64_t y = mv ? list[src] : 0ull;
+      __syncwarp();
+      if (mv) list[t] = y;
+      if (c > c_lo) below -= (uint32_t)__popc(__ballot_sync(FNB_FULL, acc && (fin >> 5) == (uint32_t)(c - 1)));
+      __syncwarp();
+    }
+    if (acc && fin < B) list[fin] = key;
+    __syncwarp();
+  }
+  len = new_len;
+  start = min(start, fin_min);
+}
+
+// ---------------------------------------------------------------------------------------------------
+template <int DT, int METRIC, int G, int CH, bool EXACT>
+__global__ void __launch_bounds__(FNB_WARPS_PER_CTA * 32, fnb_min_ctas(CH)) fnb_search_kernel(const SearchParams p) {
   extern __shared__ __align__(16) unsigned char fnb_smem[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   unsigned char* wbase = fnb_smem + (size_t)warp * p.warp_smem;
-  uint64_t* list = reinterpret_cast<uint64_t*>(wbase);
+  volatile uint64_t* list = reinterpret_cast<volatile uint64_t*>(wbase);
   uint32_t* tab = reinterpret_cast<uint32_t*>(wbase + (size_t)p.Bcap * 8);
-  uint32_t* s_ids = tab + (1u << p.hash_bits);
+  uint32_t* s_ids = tab + p.vs_buckets * 4;
   const int pos = lane % G;
 
   for (;;) {
@@ -293,7 +431,7 @@ __global__ void __launch_bounds__(FNB_WARPS_PER_CTA * 32, 3) fnb_search_kernel(c
 #pragma unroll
     for (int k = 0; k < CH; k++) q[k] = load_query_chunk<DT>(p, qi, (uint32_t)(k * G + pos));
 
-    hash_clear(tab, p.hash_bits, lane);
+    visited_clear(tab, p.vs_buckets, lane);
     __syncwarp();
 
     uint32_t ndist = 0, nhops = 0, len = 0;
@@ -304,7 +442,7 @@ __global__ void __launch_bounds__(FNB_WARPS_PER_CTA * 32, 3) fnb_search_kernel(c
       for (uint32_t base = 0; base < p.nprobe; base += 32) {
         const uint32_t pi = base + lane;
         const bool valid = pi < p.nprobe;
-        const float d = batch_distance<DT, METRIC, G, CH>(p, q, pi * p.step, valid, s_ids, lane);
+        const float d = batch_distance<DT, METRIC, G, CH, EXACT>(p, q, pi * p.step, valid, s_ids, lane, false);
         if (valid) {
           const uint64_t k = ((uint64_t)ord_f32(d) << 32) | pi;
           best = k < best ? k : best;
@@ -320,12 +458,12 @@ __global__ void __launch_bounds__(FNB_WARPS_PER_CTA * 32, 3) fnb_search_kernel(c
       const uint32_t entry = (uint32_t)best * p.step;
       if (lane == 0) {
         list[0] = (best & 0xffffffff00000000ull) | ((uint64_t)entry << 1);
-        hash_test_and_set(tab, p.hash_bits, entry);
+        visited_test_and_set(tab, p, entry);
       }
       len = 1;
       __syncwarp();
 
-      uint32_t start = 0, n_ins = 1;
+      uint32_t start = 0;
       // ---- main loop (Index.h:627-658) ----
       for (;;) {
         uint32_t cur = FNB_EMPTY;
@@ -351,76 +489,21 @@ __global__ void __launch_bounds__(FNB_WARPS_PER_CTA * 32, 3) fnb_search_kernel(c
         nhops++;
 
         for (uint32_t l0 = 0; l0 < p.M; l0 += 32) {
-          if (n_ins + 32 > p.hash_limit) {
-            // bounded reset: forget everything except the current list.  A forgotten node that is met
-            // again is re-evaluated and rejected again (its distance is >= the current worst), so results
-            // do not change; only n_dist grows.
-            hash_clear(tab, p.hash_bits, lane);
-            __syncwarp();
-            for (uint32_t i = lane; i < len; i += 32) hash_test_and_set(tab, p.hash_bits, (uint32_t)list[i] >> 1);
-            __syncwarp();
-            n_ins = len;
-          }
-          uint32_t nb = 0;
-          bool fresh = false;
-          if (l0 + lane < p.M) {
-            nb = __ldg(p.adj + (size_t)cur * p.M + l0 + lane);
-            fresh = hash_test_and_set(tab, p.hash_bits, nb);
-          }
+          uint32_t nb = cur;
+          if (l0 + lane < p.M) nb = __ldg(p.adj + (size_t)cur * p.M + l0 + lane);
+          // unused link slots are self-loops (Index.h:270): skip them without touching the visited set
+          const bool fresh = (nb != cur) && visited_test_and_set(tab, p, nb);
           const unsigned fm = __ballot_sync(FNB_FULL, fresh);
           if (!fm) continue;
-          const uint32_t nf = (uint32_t)__popc(fm);
-          n_ins += nf;
-          ndist += nf;
+          ndist += (uint32_t)__popc(fm);
           const bool full = len >= p.B;
           const uint32_t worst_hi = (uint32_t)(list[len - 1] >> 32);
 
-          const float d = batch_distance<DT, METRIC, G, CH>(p, q, nb, fresh, s_ids, lane);
+          const float d = batch_distance<DT, METRIC, G, CH, EXACT>(p, q, nb, fresh, s_ids, lane, true);
           const uint64_t key = make_key(d, nb);
           const bool acc = fresh && (!full || (uint32_t)(key >> 32) < worst_hi);
-          const unsigned am = __ballot_sync(FNB_FULL, acc);
-          if (!am) continue;
-          const uint32_t n_acc = (uint32_t)__popc(am);
-
-          // rank among the accepted, position in the list
-          uint32_t rank = 0;
-          for (unsigned m = am; m; m &= m - 1) {
-            const uint64_t kj = shfl64(key, __ffs(m) - 1);
-            rank += (kj < key) ? 1u : 0u;
-          }
-          uint32_t ipos = 0xffffffffu;
-          if (acc) {
-            uint32_t lo = 0, hi = len;
-            while (lo < hi) {
-              const uint32_t mid = (lo + hi) >> 1;
-              if (list[mid] < key) lo = mid + 1; else hi = mid;
-            }
-            ipos = lo;
-          }
-          const uint32_t fin = acc ? ipos + rank : 0xffffffffu;
-          const uint32_t pos_min = __reduce_min_sync(FNB_FULL, ipos);
-          const uint32_t fin_min = __reduce_min_sync(FNB_FULL, fin);
-          __syncwarp();
-          // shift the tail of the list, highest chunk first (in place)
-          if (pos_min < len) {
-            for (int c = (int)((len - 1) >> 5); c >= (int)(pos_min >> 5); c--) {
-              const uint32_t i = (uint32_t)c * 32 + lane;
-              const bool have = i < len && i >= pos_min;
-              const uint64_t y = have ? list[i] : 0ull;
-              uint32_t sh = 0;
-              for (unsigned m = am; m; m &= m - 1) {
-                const uint32_t pj = __shfl_sync(FNB_FULL, ipos, __ffs(m) - 1);
-                sh += (pj <= i) ? 1u : 0u;
-              }
-              __syncwarp();
-              if (have && sh > 0 && i + sh < p.B) list[i + sh] = y;
-              __syncwarp();
-            }
-          }
-          if (acc && fin < p.B) list[fin] = key;
-          __syncwarp();
-          len = min(p.B, len + n_acc);
-          start = min(start, fin_min);
+          if (!__any_sync(FNB_FULL, acc)) continue;
+          merge_accepted(list, len, start, p.B, p.Bpow2, key, acc, lane);
         }
       }
     }
@@ -449,9 +532,43 @@ __global__ void __launch_bounds__(FNB_WARPS_PER_CTA * 32, 3) fnb_search_kernel(c
 }
 
 // ---- host-side launcher -----------------------------------------------------------------------------
+// Shared memory per warp = list (Bcap*8) + visited set (buckets*16) + 128 B scratch.  The visited set takes what
+// the planned occupancy (min_ctas CTAs of 4 warps per SM) leaves of the 227 KB, up to ~48 slots per list entry
+// (~20 evaluations per unit of ef were measured on the BASELINE configs, so <= 45 % load).
+inline void size_visited(SearchParams& p, int force_buckets, int min_ctas) {
+  const uint32_t list_bytes = p.Bcap * 8u + 128u;
+  const uint32_t budget = (227u * 1024u - (uint32_t)min_ctas * 1024u) / ((uint32_t)min_ctas * FNB_WARPS_PER_CTA);  // per warp
+  uint32_t nbits = 1;
+  while ((1ull << nbits) < (uint64_t)p.N && nbits < 31) nbits++;
+  // 16-bit tags are possible when a bucket's share of the hash range fits 15 bits
+  auto tag_bits_for = [&](uint32_t buckets) {
+    uint64_t span = ((1ull << nbits) + buckets - 1) / buckets;
+    uint32_t tb = 0;
+    while ((1ull << tb) < span) tb++;
+    return tb;
+  };
+  uint32_t buckets;
+  if (force_buckets > 0) {
+    buckets = (uint32_t)force_buckets;
+  } else {
+    const uint32_t want = (p.B * 48u + 7u) / 8u;  // slots / 8 per bucket
+    const uint32_t room = budget > list_bytes ? (budget - list_bytes) / 16u : 0u;
+    buckets = want < room ? want : room;
+    if (buckets < 16u) buckets = 16u;
+  }
+  uint32_t tb = tag_bits_for(buckets);
+  p.vs_wide = tb > 15u ? 1u : 0u;
+  if (tb > 31u) tb = 31u;
+  p.vs_buckets = buckets;
+  p.vs_shift = 32u - nbits;
+  p.vs_tag_mask = (uint32_t)((1ull << tb) - 1ull);
+  p.warp_smem = (list_bytes + buckets * 16u + 15u) & ~15u;
+}
+
 template <int DT, int METRIC, int G, int CH>
 cudaError_t launch_search(const SearchParams& p, int num_sms, cudaStream_t stream) {
-  auto kern = fnb_search_kernel<DT, METRIC, G, CH>;
+  const bool exact = p.nchunks == (uint32_t)(G * CH);
+  auto kern = exact ? fnb_search_kernel<DT, METRIC, G, CH, true> : fnb_search_kernel<DT, METRIC, G, CH, false>;
   const size_t smem = (size_t)p.warp_smem * FNB_WARPS_PER_CTA;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;

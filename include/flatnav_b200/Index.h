@@ -1,0 +1,157 @@
+// C++ surface of the B200 engine: a header-only shim with the shape of the reference's
+// `flatnav::Index<dist_t, label_t>` (include/flatnav/index/Index.h:36-927 of BlaiseMuhirwa/flatnav), search side,
+// written on top of the C ABI (include/flatnav_b200.h).  Code such as the reference's tools/query_npy.cpp:43-68
+// or include/flatnav/tests/test_serialization.cpp:50-75 compiles against it after changing the include and the
+// namespace (or with -DFLATNAV_B200_AS_FLATNAV, which aliases `flatnav` to this namespace):
+//
+//   auto index = Index<SquaredL2Distance<DataType::float32>, int>::loadIndex("graph.idx");
+//   std::vector<std::pair<float, int>> top = index->search(query, /*K=*/10, /*ef_search=*/100);
+//
+// Kept from the reference: loadIndex / search / saveIndex / setNumThreads / getNumThreads and the getters
+// (Index.h:442-531), their exceptions (std::runtime_error for I/O, std::invalid_argument for bad arguments)
+// and move-only ownership.  Added: searchBatch (what bindings.cpp:161-228 does with a thread pool).
+// Not provided (outside the hot path): the constructing constructor, add/addBatch, reordering.
+#pragma once
+
+#include <algorithm>
+#include <cstdint>
+#include <limits>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <thread>
+#include <type_traits>
+#include <utility>
+#include <vector>
+
+#include "../flatnav_b200.h"
+
+namespace flatnav_b200 {
+
+namespace util {
+// include/flatnav/util/Datatype.h:11-24 — the values are part of the file format
+enum class DataType { uint8 = 0, uint16, uint32, uint64, int8, int16, int32, int64, float16, float32, float64, undefined };
+}  // namespace util
+
+namespace distances {
+using util::DataType;
+enum class MetricType { L2 = 0, IP = 1 };  // DistanceInterface.h
+
+// Tag types standing where SquaredL2Distance<data_type> / InnerProductDistance<data_type>
+// (distances/SquaredL2Distance.h:24, InnerProductDistance.h:23) stand in the reference: on the GPU the
+// arithmetic lives in the kernels, the type only selects metric and element type.
+template <DataType data_type = DataType::float32>
+struct SquaredL2Distance {
+  static constexpr int metric = FNB_METRIC_L2;
+  static constexpr DataType dtype = data_type;
+};
+template <DataType data_type = DataType::float32>
+struct InnerProductDistance {
+  static constexpr int metric = FNB_METRIC_IP;
+  static constexpr DataType dtype = data_type;
+};
+}  // namespace distances
+
+template <typename dist_t, typename label_t = int>
+class Index {
+  static_assert(std::is_same<label_t, int>::value || std::is_same<label_t, int32_t>::value,
+                "the index file stores 32-bit labels (Index.h:566-573)");
+  typedef std::pair<float, label_t> dist_label_t;
+
+ public:
+  Index(const Index&) = delete;
+  Index& operator=(const Index&) = delete;
+  Index(Index&& o) noexcept : _h(o._h), _info(o._info), _num_threads(o._num_threads) { o._h = nullptr; }
+  Index& operator=(Index&& o) noexcept {
+    if (this != &o) {
+      fnb_index_free(_h);
+      _h = o._h;
+      _info = o._info;
+      _num_threads = o._num_threads;
+      o._h = nullptr;
+    }
+    return *this;
+  }
+  ~Index() { fnb_index_free(_h); }
+
+  // Index.h:442-479.  `devices`: optional list of CUDA devices to replicate the index on.
+  static std::unique_ptr<Index<dist_t, label_t>> loadIndex(const std::string& filename,
+                                                           const std::vector<int>& devices = {}) {
+    fnb_index* h = nullptr;
+    int rc = fnb_index_load(filename.c_str(), dist_t::metric, static_cast<int>(dist_t::dtype),
+                            devices.empty() ? nullptr : devices.data(), static_cast<int>(devices.size()), &h);
+    raise(rc);
+    std::unique_ptr<Index<dist_t, label_t>> index(new Index<dist_t, label_t>());
+    index->_h = h;
+    raise(fnb_index_info(h, &index->_info));
+    index->_num_threads = std::max((uint32_t)1, (uint32_t)std::thread::hardware_concurrency() / 2);  // Index.h:467
+    return index;
+  }
+
+  // Index.h:481-490
+  void saveIndex(const std::string& filename) { raise(fnb_index_save(_h, filename.c_str())); }
+
+  // Index.h:387-409: at most K (distance, label) pairs, ascending distance.
+  std::vector<dist_label_t> search(const void* query, const int K, int ef_search, int num_initializations = 100) {
+    std::vector<float> d(static_cast<size_t>(std::max(K, 0)));
+    std::vector<int32_t> l(d.size());
+    int rc = fnb_search(_h, query, 1, K, ef_search, num_initializations, d.data(), l.data(), nullptr);
+    if (rc != FNB_SHORT_RESULT) raise(rc);
+    std::vector<dist_label_t> out;
+    out.reserve(d.size());
+    for (size_t i = 0; i < d.size(); i++) {
+      if (l[i] < 0 && d[i] == std::numeric_limits<float>::infinity()) break;  // fewer than K reachable
+      out.emplace_back(d[i], static_cast<label_t>(l[i]));
+    }
+    return out;
+  }
+
+  // The batched fan-out of the Python binding (bindings.cpp:161-228) as one call: queries is row-major
+  // [num_queries, dim] of the index element type; distances / labels are [num_queries, K].
+  // Throws std::runtime_error if any query found fewer than K results (bindings.cpp:184-189).
+  void searchBatch(const void* queries, size_t num_queries, int K, int ef_search, float* distances, label_t* labels,
+                   int num_initializations = 100, fnb_search_stats* stats = nullptr) {
+    raise(fnb_search(_h, queries, static_cast<int64_t>(num_queries), K, ef_search, num_initializations, distances,
+                     reinterpret_cast<int32_t*>(labels), stats));
+  }
+
+  // Index.h:492-503 — validated like the reference; GPU execution does not use it.
+  inline void setNumThreads(uint32_t num_threads) {
+    if (num_threads == 0 || num_threads > std::thread::hardware_concurrency()) {
+      throw std::invalid_argument(
+          "Number of threads must be greater than 0 and less than or equal to the number of hardware threads.");
+    }
+    _num_threads = num_threads;
+  }
+  inline uint32_t getNumThreads() const { return _num_threads; }
+
+  // Index.h:519-531
+  inline size_t maxEdgesPerNode() const { return _info.max_edges_per_node; }
+  inline size_t dataSizeBytes() const { return _info.data_size_bytes; }
+  inline size_t nodeSizeBytes() const { return _info.node_size_bytes; }
+  inline size_t maxNodeCount() const { return _info.max_node_count; }
+  inline size_t currentNumNodes() const { return _info.cur_num_nodes; }
+  inline size_t dataDimension() const { return _info.dim; }
+  inline util::DataType getDataType() const { return static_cast<util::DataType>(_info.data_type); }
+  inline uint64_t getTotalIndexMemory() const { return _info.node_size_bytes * _info.max_node_count; }
+  inline const fnb_info& deviceInfo() const { return _info; }
+  fnb_index* handle() { return _h; }
+
+ private:
+  Index() = default;
+  static void raise(int rc) {
+    if (rc == FNB_OK) return;
+    const std::string msg = fnb_last_error();
+    if (rc == FNB_ERR_INVALID_ARG) throw std::invalid_argument(msg);
+    throw std::runtime_error(msg);
+  }
+  fnb_index* _h = nullptr;
+  fnb_info _info{};
+  uint32_t _num_threads = 1;
+};
+
+}  // namespace flatnav_b200
+
+#ifdef FLATNAV_B200_AS_FLATNAV
+namespace flatnav = flatnav_b200;
+#endif

@@ -1,0 +1,88 @@
+// Exercises the C++ shim (include/flatnav_b200/Index.h) the way the reference's own C++ callers use
+// flatnav::Index (tools/query_npy.cpp:43-68, include/flatnav/tests/test_serialization.cpp:50-75).
+// usage: shim_test <index.idx> <queries.f32> <Q> <K> <ef> <out_prefix>
+#define FLATNAV_B200_AS_FLATNAV
+#include <flatnav_b200/Index.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+
+using flatnav::Index;
+using flatnav::distances::SquaredL2Distance;
+using flatnav::util::DataType;
+
+int main(int argc, char** argv) {
+  if (argc < 7) return 2;
+  const std::string idx = argv[1], qpath = argv[2], out = argv[6];
+  const size_t Q = std::strtoull(argv[3], nullptr, 10);
+  const int K = std::atoi(argv[4]), ef = std::atoi(argv[5]);
+  int checks = 0;
+
+  try {
+    Index<SquaredL2Distance<DataType::float32>, int>::loadIndex("/nonexistent/x.idx");
+    return 10;
+  } catch (const std::runtime_error&) { checks++; }
+
+  auto index = Index<SquaredL2Distance<DataType::float32>, int>::loadIndex(idx);
+  const size_t D = index->dataDimension();
+  if (index->nodeSizeBytes() != index->dataSizeBytes() + 4 * index->maxEdgesPerNode() + 4) return 11;  // test_serialization.cpp:56
+  if (index->getDataType() != DataType::float32) return 12;
+
+  std::vector<float> q(Q * D);
+  std::ifstream f(qpath, std::ios::binary);
+  f.read((char*)q.data(), (std::streamsize)(q.size() * sizeof(float)));
+
+  try {
+    index->search(q.data(), K, ef, 0);
+    return 13;
+  } catch (const std::invalid_argument&) { checks++; }  // Index.h:847-849
+  try {
+    index->setNumThreads(0);
+    return 14;
+  } catch (const std::invalid_argument&) { checks++; }  // Index.h:493-497
+
+  // one query at a time, like tools/query_npy.cpp:51
+  std::vector<float> d1(Q * K);
+  std::vector<int> l1(Q * K);
+  for (size_t i = 0; i < Q; i++) {
+    auto r = index->search(q.data() + i * D, K, ef);
+    if ((int)r.size() != K) return 15;
+    for (int j = 0; j < K; j++) {
+      d1[i * K + j] = r[j].first;
+      l1[i * K + j] = r[j].second;
+    }
+  }
+  // batched
+  std::vector<float> d2(Q * K);
+  std::vector<int> l2(Q * K);
+  index->searchBatch(q.data(), Q, K, ef, d2.data(), l2.data());
+  if (d1 != d2 || l1 != l2) return 16;
+
+  // save -> load -> identical results (test_serialization.cpp:64-75)
+  index->saveIndex(out + ".resaved.idx");
+  auto again = Index<SquaredL2Distance<DataType::float32>, int>::loadIndex(out + ".resaved.idx");
+  std::vector<float> d3(Q * K);
+  std::vector<int> l3(Q * K);
+  again->searchBatch(q.data(), Q, K, ef, d3.data(), l3.data());
+  if (d3 != d2 || l3 != l2) return 17;
+
+  // more results than nodes: search() returns fewer than K, searchBatch throws (bindings.cpp:184-189)
+  auto few = index->search(q.data(), (int)index->currentNumNodes() + 3, 8);
+  if (few.size() > index->currentNumNodes()) return 18;
+  try {
+    std::vector<float> dd(Q * (index->currentNumNodes() + 3));
+    std::vector<int> ll(dd.size());
+    index->searchBatch(q.data(), Q, (int)index->currentNumNodes() + 3, 8, dd.data(), ll.data());
+    return 19;
+  } catch (const std::runtime_error&) { checks++; }
+
+  auto moved = std::move(*index);  // move-only ownership (Index.h:86-132)
+  if (moved.currentNumNodes() == 0) return 20;
+
+  std::ofstream fd(out + ".dist.bin", std::ios::binary), fl(out + ".label.bin", std::ios::binary);
+  fd.write((const char*)d2.data(), (std::streamsize)(d2.size() * sizeof(float)));
+  fl.write((const char*)l2.data(), (std::streamsize)(l2.size() * sizeof(int)));
+  std::printf("shim ok, %d exception checks\n", checks);
+  return 0;
+}

@@ -88,3 +88,15 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src and "liboracle" not in src, f
+
+
+def test_cpp_shim_compiles_and_links(tmp_path):
+    """the C++ surface (include/flatnav_b200/Index.h) builds against the C ABI with plain g++"""
+    import subprocess
+    exe = str(tmp_path / "shim_test")
+    subprocess.run(["g++", "-std=c++17", "-O2", "-Wall", "-I" + os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "cpp", "shim_test.cpp"), "-o", exe,
+                    "-L" + os.path.join(ROOT, "flatnav_b200"), "-lflatnav_b200",
+                    "-Wl,-rpath," + os.path.join(ROOT, "flatnav_b200")], check=True)
+    r = subprocess.run([exe], capture_output=True)
+    assert r.returncode == 2  # usage

@@ -54,9 +54,13 @@ def test_cuda_bit_exact_vs_oracle(case):
         do, lo, nd, nh = ora.search(g["queries"], K, ef, mode=port.MODE_LIST, dist_order=port.ORDER_LANES, counters=True)
         np.testing.assert_array_equal(d.view(np.uint32), do.view(np.uint32))
         np.testing.assert_array_equal(l, lo)
-        assert ix.last_stats["n_dist"] == int(nd.sum()) and ix.last_stats["n_hops"] == int(nh.sum())
+        # the visited set never reports a false positive but may forget: every hop is identical, and the number
+        # of distance evaluations is the oracle's plus a small re-evaluation overhead
+        assert ix.last_stats["n_hops"] == int(nh.sum())
+        assert int(nd.sum()) <= ix.last_stats["n_dist"] <= int(nd.sum()) * 1.02 + 8
         Q = g["queries"].shape[0]
-        assert ix.last_stats["algo_bytes"] == int(nd.sum()) * ora.data_size_bytes + int(nh.sum()) * ora.M * 4 + \
+        st = ix.last_stats
+        assert st["algo_bytes"] == st["n_dist"] * ora.data_size_bytes + st["n_hops"] * ora.M * 4 + \
             Q * ora.data_size_bytes + Q * K * 8
 
 
@@ -109,27 +113,27 @@ def test_cuda_vs_live_reference_and_oracle(ref_cache, metric, gen, dim, n, M):
             assert abs(recall(l, gt_l) - recall(lr, gt_l)) <= 0.002
 
 
-def test_large_ef_forces_hash_resets(ref_cache):
-    """ef far above the sizing heuristic: the bounded visited-hash reset must not change results"""
+def test_tiny_visited_set_and_large_ef(ref_cache):
+    """a deliberately tiny visited set forgets constantly: results must not change, only n_dist grows"""
     path = build_ref_index(ref_cache, "l2", "latent", 20000, 128, 32, 100)
     q = synthetic.make("latent", 64, 128, queries=True)
     ix = flatnav_b200.index.IndexL2Float.load_index(path)
     ora = port.OracleIndex(path, port.L2)
-    old = os.environ.get("FNB_HASH_BITS")
+    old = os.environ.get("FNB_VS_BUCKETS")
     try:
-        os.environ["FNB_HASH_BITS"] = "9"  # 512 slots: resets every few expansions
+        os.environ["FNB_VS_BUCKETS"] = "16"  # 128 slots: forgets almost everything
         d, l = ix.search(q, 10, 100)
         stats_small = dict(ix.last_stats)
     finally:
         if old is None:
-            os.environ.pop("FNB_HASH_BITS", None)
+            os.environ.pop("FNB_VS_BUCKETS", None)
         else:
-            os.environ["FNB_HASH_BITS"] = old
+            os.environ["FNB_VS_BUCKETS"] = old
     do, lo, nd, nh = ora.search(q, 10, 100, mode=port.MODE_LIST, counters=True)
     np.testing.assert_array_equal(d.view(np.uint32), do.view(np.uint32))
     np.testing.assert_array_equal(l, lo)
     assert stats_small["n_hops"] == int(nh.sum())
-    assert stats_small["n_dist"] >= int(nd.sum())  # forgotten nodes are re-evaluated, never re-admitted
+    assert stats_small["n_dist"] > int(nd.sum())  # forgotten nodes are re-evaluated, never re-admitted
     d2, l2 = ix.search(q, 10, 2000)
     do2, lo2 = ora.search(q, 10, 2000, mode=port.MODE_LIST)
     np.testing.assert_array_equal(d2.view(np.uint32), do2.view(np.uint32))
@@ -268,3 +272,30 @@ def test_merge_topk_kernel():
         exp = pairs[:K]
         got = list(zip(od[qi].tolist(), ol[qi].tolist()))
         assert got == exp
+
+
+def test_cpp_shim_end_to_end(tmp_path):
+    """include/flatnav_b200/Index.h used like the reference's C++ callers use flatnav::Index"""
+    import subprocess
+    from conftest import ROOT
+    case = CASES[0]
+    g = golden_arrays(case["name"])
+    exe = str(tmp_path / "shim_test")
+    subprocess.run(["g++", "-std=c++17", "-O2", "-I" + os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "cpp", "shim_test.cpp"), "-o", exe,
+                    "-L" + os.path.join(ROOT, "flatnav_b200"), "-lflatnav_b200",
+                    "-Wl,-rpath," + os.path.join(ROOT, "flatnav_b200")], check=True)
+    qp = str(tmp_path / "q.bin")
+    g["queries"].tofile(qp)
+    K, ef = case["runs"][0]
+    out = str(tmp_path / "out")
+    r = subprocess.run([exe, golden_index_path(case["name"]), qp, str(g["queries"].shape[0]), str(K), str(ef), out],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    assert "shim ok, 4 exception checks" in r.stdout
+    d = np.fromfile(out + ".dist.bin", dtype=np.float32).reshape(-1, K)
+    l = np.fromfile(out + ".label.bin", dtype=np.int32).reshape(-1, K)
+    do, lo = port.OracleIndex(golden_index_path(case["name"]), port.L2).search(g["queries"], K, ef, mode=port.MODE_LIST)
+    np.testing.assert_array_equal(d.view(np.uint32), do.view(np.uint32))
+    np.testing.assert_array_equal(l, lo)
+    assert rel_err(d, g[f"dist_k{K}_ef{ef}"]) <= 1e-5
