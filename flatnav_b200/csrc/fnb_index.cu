@@ -151,6 +151,7 @@ static int upload_replica(const Header& h, const unsigned char* blob, int device
   CU(cudaMalloc(&r->labels, n * 4));
   CU(cudaMalloc(&r->counter, 64));
   CU(cudaMalloc(&r->totals, 64));
+  CU(cudaMallocHost(&r->h_totals, 64));
   CU(cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking));
   CU(cudaEventCreate(&r->ev[0]));
   CU(cudaEventCreate(&r->ev[1]));
@@ -185,6 +186,7 @@ static void free_replica(Replica* r) {
   cudaFree(r->labels);
   cudaFree(r->counter);
   cudaFree(r->totals);
+  if (r->h_totals) cudaFreeHost(r->h_totals);
   cudaFree(r->ws);
   if (r->h_pinned) cudaFreeHost(r->h_pinned);
   if (r->stream) cudaStreamDestroy(r->stream);
@@ -423,6 +425,7 @@ int fnb_search_device(fnb_index* ix, int replica, const void* d_queries, int64_t
   p.adj = r.adj;
   p.labels = r.labels;
   p.queries = d_queries;
+  if (((uintptr_t)d_queries & 15u) != 0) p.query_vec_ok = 0;
   p.out_dist = d_out_dist;
   p.out_label = d_out_label;
   p.out_ndist = d_ndist;
@@ -467,6 +470,22 @@ int fnb_search(fnb_index* ix, const void* queries, int64_t Q, int K, int ef_sear
   const int R = (int)ix->replicas.size();
   int prev = 0;
   cudaGetDevice(&prev);
+  // Page-locked caller buffers (cudaHostAlloc / cudaHostRegister, e.g. torch pinned tensors) are used in place:
+  // the kernel reads each query straight from host memory when a warp picks it up and writes the K results
+  // straight back, so the transfers overlap the traversal instead of bracketing it.  Pageable buffers are
+  // staged through device memory with asynchronous copies on the replica's stream.
+  auto mapped = [](const void* host) -> unsigned char* {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, host) != cudaSuccess) {
+      cudaGetLastError();
+      return nullptr;
+    }
+    return a.type == cudaMemoryTypeHost ? static_cast<unsigned char*>(a.devicePointer) : nullptr;
+  };
+  unsigned char* zq = getenv("FNB_NO_ZEROCOPY") ? nullptr : mapped(queries);
+  unsigned char* zd = getenv("FNB_NO_ZEROCOPY") ? nullptr : mapped(out_dist);
+  unsigned char* zl = getenv("FNB_NO_ZEROCOPY") ? nullptr : mapped(out_label);
+  if (!zd || !zl) zd = zl = nullptr;
   const int64_t per = (Q + R - 1) / R;
   struct Part {
     int64_t q0, nq;
@@ -482,27 +501,29 @@ int fnb_search(fnb_index* ix, const void* queries, int64_t Q, int K, int ef_sear
     if (pt.nq <= 0) continue;
     CU(cudaSetDevice(r.device));
     const size_t qb = (size_t)pt.nq * h.data_size, ob = (size_t)pt.nq * K * 4;
-    rc = ensure_workspace(&r, align256(qb) + 2 * align256(ob), 0);
+    rc = ensure_workspace(&r, (zq ? 0 : align256(qb)) + (zd ? 0 : 2 * align256(ob)) + 256, 0);
     if (rc != FNB_OK) {
       cudaSetDevice(prev);
       return rc;
     }
-    pt.d_q = r.ws;
-    pt.d_dist = r.ws + align256(qb);
-    pt.d_label = pt.d_dist + align256(ob);
+    pt.d_q = zq ? zq + (size_t)pt.q0 * h.data_size : r.ws;
+    pt.d_dist = zd ? zd + (size_t)pt.q0 * K * 4 : r.ws + (zq ? 0 : align256(qb));
+    pt.d_label = zd ? zl + (size_t)pt.q0 * K * 4 : pt.d_dist + align256(ob);
     SearchParams p = p0;
     p.Q = (uint32_t)pt.nq;
     p.vec = r.vec;
     p.adj = r.adj;
     p.labels = r.labels;
     p.queries = pt.d_q;
+    if (((uintptr_t)pt.d_q & 15u) != 0) p.query_vec_ok = 0;
     p.out_dist = reinterpret_cast<float*>(pt.d_dist);
     p.out_label = reinterpret_cast<int32_t*>(pt.d_label);
     p.counter = r.counter;
     p.totals = r.totals;
     CU(cudaEventRecord(r.ev[0], r.stream));
-    CU(cudaMemcpyAsync(pt.d_q, (const unsigned char*)queries + (size_t)pt.q0 * h.data_size, qb,
-                       cudaMemcpyHostToDevice, r.stream));
+    if (!zq)
+      CU(cudaMemcpyAsync(pt.d_q, (const unsigned char*)queries + (size_t)pt.q0 * h.data_size, qb,
+                         cudaMemcpyHostToDevice, r.stream));
     CU(cudaMemsetAsync(r.counter, 0, 4, r.stream));
     CU(cudaMemsetAsync(r.totals, 0, 24, r.stream));
     CU(cudaEventRecord(r.ev[1], r.stream));
@@ -512,8 +533,11 @@ int fnb_search(fnb_index* ix, const void* queries, int64_t Q, int K, int ef_sear
       return fail(FNB_ERR_CUDA, "search kernel launch failed: %s", cudaGetErrorString(e));
     }
     CU(cudaEventRecord(r.ev[2], r.stream));
-    CU(cudaMemcpyAsync(out_dist + (size_t)pt.q0 * K, pt.d_dist, ob, cudaMemcpyDeviceToHost, r.stream));
-    CU(cudaMemcpyAsync(out_label + (size_t)pt.q0 * K, pt.d_label, ob, cudaMemcpyDeviceToHost, r.stream));
+    if (!zd) {
+      CU(cudaMemcpyAsync(out_dist + (size_t)pt.q0 * K, pt.d_dist, ob, cudaMemcpyDeviceToHost, r.stream));
+      CU(cudaMemcpyAsync(out_label + (size_t)pt.q0 * K, pt.d_label, ob, cudaMemcpyDeviceToHost, r.stream));
+    }
+    CU(cudaMemcpyAsync(r.h_totals, r.totals, 24, cudaMemcpyDeviceToHost, r.stream));
     CU(cudaEventRecord(r.ev[3], r.stream));
   }
   int64_t nd = 0, nh = 0, ns = 0;
@@ -524,8 +548,7 @@ int fnb_search(fnb_index* ix, const void* queries, int64_t Q, int K, int ef_sear
     Replica& r = ix->replicas[i];
     CU(cudaSetDevice(r.device));
     CU(cudaStreamSynchronize(r.stream));
-    unsigned long long t[3];
-    CU(cudaMemcpy(t, r.totals, sizeof(t), cudaMemcpyDeviceToHost));
+    const unsigned long long* t = r.h_totals;
     nd += (int64_t)t[0];
     nh += (int64_t)t[1];
     ns += (int64_t)t[2];

@@ -29,6 +29,7 @@ struct Replica {
   int32_t* labels = nullptr;
   unsigned int* counter = nullptr;
   unsigned long long* totals = nullptr;
+  unsigned long long* h_totals = nullptr;  // pinned mirror of `totals`
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   unsigned char* ws = nullptr;  // device workspace of the host-buffer entry points

@@ -239,11 +239,19 @@ __device__ __forceinline__ float batch_distance(const SearchParams& p, const uin
   __syncwarp();
   const int g = lane / G, pos = lane % G;
   if (prefetch && n > RPI * U) {
-    for (int c0 = RPI * U; c0 < n; c0 += RPI) {
-      const int c = c0 + g;
-      if (c < n) {
-        const uint4* row = p.vec + (size_t)s_ids[c] * p.stride;
-        for (uint32_t line = (uint32_t)pos; line < p.lines_per_row; line += G) prefetch_l2(row + line * 8u);
+    if (p.lines_per_row <= (uint32_t)G) {  // one 128-byte line per lane of the group: a single predicated prefetch
+      const bool mine_line = (uint32_t)pos < p.lines_per_row;
+      for (int c0 = RPI * U; c0 < n; c0 += RPI) {
+        const int c = c0 + g;
+        if (mine_line && c < n) prefetch_l2(p.vec + (size_t)s_ids[c] * p.stride + pos * 8);
+      }
+    } else {
+      for (int c0 = RPI * U; c0 < n; c0 += RPI) {
+        const int c = c0 + g;
+        if (c < n) {
+          const uint4* row = p.vec + (size_t)s_ids[c] * p.stride;
+          for (uint32_t line = (uint32_t)pos; line < p.lines_per_row; line += G) prefetch_l2(row + line * 8u);
+        }
       }
     }
   }
@@ -537,7 +545,6 @@ __global__ void __launch_bounds__(FNB_WARPS_PER_CTA * 32, fnb_min_ctas(CH)) fnb_
 // (~20 evaluations per unit of ef were measured on the BASELINE configs, so <= 45 % load).
 inline void size_visited(SearchParams& p, int force_buckets, int min_ctas) {
   const uint32_t list_bytes = p.Bcap * 8u + 128u;
-  const uint32_t budget = (227u * 1024u - (uint32_t)min_ctas * 1024u) / ((uint32_t)min_ctas * FNB_WARPS_PER_CTA);  // per warp
   uint32_t nbits = 1;
   while ((1ull << nbits) < (uint64_t)p.N && nbits < 31) nbits++;
   // 16-bit tags are possible when a bucket's share of the hash range fits 15 bits
@@ -551,9 +558,18 @@ inline void size_visited(SearchParams& p, int force_buckets, int min_ctas) {
   if (force_buckets > 0) {
     buckets = (uint32_t)force_buckets;
   } else {
-    const uint32_t want = (p.B * 48u + 7u) / 8u;  // slots / 8 per bucket
-    const uint32_t room = budget > list_bytes ? (budget - list_bytes) / 16u : 0u;
-    buckets = want < room ? want : room;
+    // Full size: ~48 slots per list entry.  Occupancy is worth more than a roomy set (a forgotten node costs one
+    // extra row fetch; measured +1.5 % evaluations at 1 slot per visit), so the planned CTA count is only
+    // lowered when the set would fall below 8 slots per list entry (large ef: the list itself eats the budget).
+    const uint32_t want = (p.B * 48u + 7u) / 8u;
+    const uint32_t floor_b = want < p.B ? want : p.B;
+    buckets = 16u;
+    for (int c = min_ctas; c >= 1; c--) {
+      const uint32_t budget = (227u * 1024u - (uint32_t)c * 1024u) / ((uint32_t)c * FNB_WARPS_PER_CTA);  // per warp
+      const uint32_t room = budget > list_bytes ? (budget - list_bytes) / 16u : 0u;
+      buckets = want < room ? want : room;
+      if (buckets >= floor_b || c == 1) break;
+    }
     if (buckets < 16u) buckets = 16u;
   }
   uint32_t tb = tag_bits_for(buckets);
