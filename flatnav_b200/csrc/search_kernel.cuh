@@ -558,11 +558,13 @@ inline void size_visited(SearchParams& p, int force_buckets, int min_ctas) {
   if (force_buckets > 0) {
     buckets = (uint32_t)force_buckets;
   } else {
-    // Full size: ~48 slots per list entry.  Occupancy is worth more than a roomy set (a forgotten node costs one
-    // extra row fetch; measured +1.5 % evaluations at 1 slot per visit), so the planned CTA count is only
-    // lowered when the set would fall below 8 slots per list entry (large ef: the list itself eats the budget).
+    // Full size: ~48 slots per list entry.  Resident warps are worth far more than a roomy set: the traversal is
+    // latency-bound per warp, and a forgotten node only costs one extra row fetch (measured at ef=1000 on
+    // 1M x 128: 6 CTAs/SM with a set so small that n_dist grows 64 % is still 1.9x faster than 2 CTAs/SM with a
+    // full-size set).  So the planned CTA count is lowered only when the LIST no longer fits beside a minimal
+    // set of one slot per list entry.
     const uint32_t want = (p.B * 48u + 7u) / 8u;
-    const uint32_t floor_b = want < p.B ? want : p.B;
+    const uint32_t floor_b = p.B / 8u > 16u ? p.B / 8u : 16u;
     buckets = 16u;
     for (int c = min_ctas; c >= 1; c--) {
       const uint32_t budget = (227u * 1024u - (uint32_t)c * 1024u) / ((uint32_t)c * FNB_WARPS_PER_CTA);  // per warp
