@@ -38,6 +38,17 @@ class FnbSearchStats(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
 
 
+class FnbBfStats(C.Structure):
+    _fields_ = [
+        ("path", C.c_int32), ("reserved", C.c_int32), ("n_unsafe", C.c_int64), ("n_candidates", C.c_int64),
+        ("prep_ms", C.c_float), ("gemm_ms", C.c_float), ("rerank_ms", C.c_float), ("rescan_ms", C.c_float),
+        ("gemm_flops", C.c_double),
+    ]
+
+    def as_dict(self) -> dict:
+        return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+
+
 EXPORTS = {
     # name: (restype, argtypes)
     "fnb_index_load": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_void_p)]),
@@ -53,6 +64,7 @@ EXPORTS = {
     "fnb_search_device_totals": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
                                            C.POINTER(C.c_int64)]),
     "fnb_bruteforce": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),
+    "fnb_bruteforce_stats": (C.c_int, [C.POINTER(FnbBfStats)]),
     "fnb_merge_topk": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_void_p, C.c_void_p,
                                  C.c_void_p]),
     "fnb_last_error": (C.c_char_p, []),

@@ -9,21 +9,12 @@
 // CUDA-core version: one warp per query, a CTA of 8 warps streams the database through a shared-memory
 // tile that all 8 queries reuse.
 #include "../../include/flatnav_b200.h"
-#include "fnb_internal.h"
+#include <cstdlib>
+#include <cstring>
+
+#include "bf_common.cuh"
 
 namespace fnb {
-
-#define BF_WARPS 8
-#define BF_TILE_ROWS 32
-
-struct BfParams {
-  const uint4* __restrict__ vec;
-  const int32_t* __restrict__ labels;
-  const void* __restrict__ queries;
-  float* __restrict__ out_dist;
-  int32_t* __restrict__ out_label;
-  uint32_t N, dim, nchunks, stride, Q, K, Kcap, query_vec_ok;
-};
 
 template <int DT, int METRIC, int G, int CH>
 __global__ void __launch_bounds__(BF_WARPS * 32) bruteforce_kernel(const BfParams p) {
@@ -35,8 +26,9 @@ __global__ void __launch_bounds__(BF_WARPS * 32) bruteforce_kernel(const BfParam
   const int g = lane / G, pos = lane % G;
   constexpr int RPI = 32 / G;
   uint64_t* list = lists + (size_t)warp * p.Kcap;
-  const uint32_t qi = blockIdx.x * BF_WARPS + warp;
-  const bool active = qi < p.Q;
+  const uint32_t slot = blockIdx.x * BF_WARPS + warp;
+  const bool active = slot < p.Q;
+  const uint32_t qi = (active && p.qmap) ? p.qmap[slot] : slot;
 
   SearchParams sp;  // only the fields load_query_chunk reads
   sp.queries = p.queries;
@@ -74,24 +66,7 @@ __global__ void __launch_bounds__(BF_WARPS * 32) bruteforce_kernel(const BfParam
       const bool cand = ok && pos == 0 && (len < p.K || key < worst);
       unsigned cm = __ballot_sync(FNB_FULL, cand);
       for (; cm; cm &= cm - 1) {  // rare after the first few tiles: sequential warp-parallel insertion
-        const uint64_t kx = shfl64(key, __ffs(cm) - 1);
-        if (len >= p.K && !(kx < list[len - 1])) continue;
-        uint32_t cnt = 0;
-        for (uint32_t i = lane; i < len; i += 32) cnt += (list[i] < kx) ? 1u : 0u;
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) cnt += __shfl_xor_sync(FNB_FULL, cnt, off);
-        const uint32_t ins = cnt;
-        for (int c = (int)((len ? len - 1 : 0) >> 5); c >= (int)(ins >> 5) && len; c--) {
-          const uint32_t i = (uint32_t)c * 32 + lane;
-          const bool have = i < len && i >= ins;
-          const uint64_t y = have ? list[i] : 0ull;
-          __syncwarp();
-          if (have && i + 1 < p.K) list[i + 1] = y;
-          __syncwarp();
-        }
-        if (lane == 0) list[ins] = kx;
-        __syncwarp();
-        len = min(p.K, len + 1);
+        warp_topk_insert(list, len, p.K, shfl64(key, __ffs(cm) - 1), lane);
       }
     }
   }
@@ -137,6 +112,17 @@ static cudaError_t bf_gc(const fnb_index* ix, const BfParams& p, cudaStream_t s)
   return launch_bf<DT, METRIC, 32, 16>(p, s);
 }
 
+cudaError_t launch_exact_scan(const fnb_index* ix, const BfParams& p, cudaStream_t s) {
+  const bool ip = ix->h.metric == FNB_METRIC_IP;
+  switch (ix->h.data_type) {
+    case FNB_DTYPE_FLOAT32: return ip ? bf_gc<DT_F32, M_IP>(ix, p, s) : bf_gc<DT_F32, M_L2>(ix, p, s);
+    case FNB_DTYPE_UINT8: return ip ? bf_gc<DT_U8, M_IP>(ix, p, s) : bf_gc<DT_U8, M_L2>(ix, p, s);
+    default: return ip ? bf_gc<DT_I8, M_IP>(ix, p, s) : bf_gc<DT_I8, M_L2>(ix, p, s);
+  }
+}
+
+static thread_local BfRun g_last_bf;
+
 }  // namespace fnb
 
 using namespace fnb;
@@ -148,6 +134,7 @@ extern "C" int fnb_bruteforce(fnb_index* ix, const void* queries, int64_t Q, int
   if (Q == 0) return FNB_OK;
   if (!queries || !out_dist || !out_label) return fail(FNB_ERR_INVALID_ARG, "NULL buffer");
   if (K > 2048) return fail(FNB_ERR_UNSUPPORTED, "brute force supports K <= 2048");
+  if (Q >= (1ll << 31)) return fail(FNB_ERR_UNSUPPORTED, "more than 2^31 queries in one call");
   std::lock_guard<std::mutex> lock(ix->mu);
   Replica& r = ix->replicas[0];
   const Header& h = ix->h;
@@ -168,34 +155,70 @@ extern "C" int fnb_bruteforce(fnb_index* ix, const void* queries, int64_t Q, int
   BF_CU(cudaMalloc(&d_d, ob));
   BF_CU(cudaMalloc(&d_l, ob));
   BF_CU(cudaMemcpyAsync(d_q, queries, qb, cudaMemcpyHostToDevice, r.stream));
-  BfParams p;
-  p.vec = r.vec;
-  p.labels = r.labels;
-  p.queries = d_q;
-  p.out_dist = reinterpret_cast<float*>(d_d);
-  p.out_label = reinterpret_cast<int32_t*>(d_l);
-  p.N = (uint32_t)h.cur_nodes;
-  p.dim = (uint32_t)h.dim;
-  p.nchunks = ix->nchunks;
-  p.stride = ix->stride;
-  p.Q = (uint32_t)Q;
-  p.K = (uint32_t)K;
-  p.Kcap = ((uint32_t)K + 31u) & ~31u;
-  p.query_vec_ok = (h.data_size % FNB_CHUNK_BYTES) == 0 ? 1u : 0u;
-  const bool ip = h.metric == FNB_METRIC_IP;
-  cudaError_t e;
-  switch (h.data_type) {
-    case FNB_DTYPE_FLOAT32: e = ip ? bf_gc<DT_F32, M_IP>(ix, p, r.stream) : bf_gc<DT_F32, M_L2>(ix, p, r.stream); break;
-    case FNB_DTYPE_UINT8: e = ip ? bf_gc<DT_U8, M_IP>(ix, p, r.stream) : bf_gc<DT_U8, M_L2>(ix, p, r.stream); break;
-    default: e = ip ? bf_gc<DT_I8, M_IP>(ix, p, r.stream) : bf_gc<DT_I8, M_L2>(ix, p, r.stream); break;
+  // FNB_BF_MODE=exact|tensor forces a path (tests, profiling); default: the tcgen05 filter + exact re-rank
+  // whenever the problem is large enough to fill tensor-core tiles.
+  const char* mode = getenv("FNB_BF_MODE");
+  const bool force_exact = mode && !strcmp(mode, "exact");
+  const bool force_tensor = mode && !strcmp(mode, "tensor");
+  BfRun run;
+  int rc = FNB_OK;
+  if (!force_exact && tensor_path_supported(ix, Q, K) &&
+      (force_tensor || ((double)Q * (double)h.cur_nodes >= 1e8 && h.cur_nodes >= 4096))) {
+    run.path = 1;
+    rc = bruteforce_tensor(ix, r, d_q, Q, K, reinterpret_cast<float*>(d_d), reinterpret_cast<int32_t*>(d_l), &run);
+  } else if (force_tensor) {
+    rc = fail(FNB_ERR_UNSUPPORTED, "FNB_BF_MODE=tensor but the tensor path does not support this problem (K=%d)", K);
+  } else {
+    BfParams p;
+    memset(&p, 0, sizeof(p));
+    p.vec = r.vec;
+    p.labels = r.labels;
+    p.queries = d_q;
+    p.qmap = nullptr;
+    p.out_dist = reinterpret_cast<float*>(d_d);
+    p.out_label = reinterpret_cast<int32_t*>(d_l);
+    p.N = (uint32_t)h.cur_nodes;
+    p.dim = (uint32_t)h.dim;
+    p.nchunks = ix->nchunks;
+    p.stride = ix->stride;
+    p.Q = (uint32_t)Q;
+    p.K = (uint32_t)K;
+    p.Kcap = ((uint32_t)K + 31u) & ~31u;
+    p.query_vec_ok = (h.data_size % FNB_CHUNK_BYTES) == 0 ? 1u : 0u;
+    cudaEvent_t e0, e1;
+    BF_CU(cudaEventCreate(&e0));
+    BF_CU(cudaEventCreate(&e1));
+    BF_CU(cudaEventRecord(e0, r.stream));
+    BF_CU(launch_exact_scan(ix, p, r.stream));
+    BF_CU(cudaEventRecord(e1, r.stream));
+    BF_CU(cudaEventSynchronize(e1));
+    cudaEventElapsedTime(&run.rescan_ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
   }
-  BF_CU(e);
-  BF_CU(cudaMemcpyAsync(out_dist, d_d, ob, cudaMemcpyDeviceToHost, r.stream));
-  BF_CU(cudaMemcpyAsync(out_label, d_l, ob, cudaMemcpyDeviceToHost, r.stream));
-  BF_CU(cudaStreamSynchronize(r.stream));
+  if (rc == FNB_OK) {
+    BF_CU(cudaMemcpyAsync(out_dist, d_d, ob, cudaMemcpyDeviceToHost, r.stream));
+    BF_CU(cudaMemcpyAsync(out_label, d_l, ob, cudaMemcpyDeviceToHost, r.stream));
+    BF_CU(cudaStreamSynchronize(r.stream));
+  }
   cudaFree(d_q);
   cudaFree(d_d);
   cudaFree(d_l);
   cudaSetDevice(prev);
+  g_last_bf = run;
+  return rc;
+}
+
+extern "C" int fnb_bruteforce_stats(fnb_bf_stats* out) {
+  if (!out) return fail(FNB_ERR_INVALID_ARG, "NULL argument");
+  memset(out, 0, sizeof(*out));
+  out->path = g_last_bf.path;
+  out->n_unsafe = g_last_bf.n_unsafe;
+  out->n_candidates = g_last_bf.n_candidates;
+  out->prep_ms = g_last_bf.prep_ms;
+  out->gemm_ms = g_last_bf.gemm_ms;
+  out->rerank_ms = g_last_bf.rerank_ms;
+  out->rescan_ms = g_last_bf.rescan_ms;
+  out->gemm_flops = g_last_bf.gemm_flops;
   return FNB_OK;
 }

@@ -124,7 +124,11 @@ class _GpuIndex:
         Q = q.shape[0]
         dist = np.empty((Q, K), dtype=np.float32)
         lab = np.empty((Q, K), dtype=np.int32)
-        _capi.check(_capi.lib().fnb_bruteforce(self._h, q.ctypes.data, Q, int(K), dist.ctypes.data, lab.ctypes.data))
+        rc = _capi.lib().fnb_bruteforce(self._h, q.ctypes.data, Q, int(K), dist.ctypes.data, lab.ctypes.data)
+        st = _capi.FnbBfStats()
+        _capi.lib().fnb_bruteforce_stats(C.byref(st))
+        self.last_bruteforce_stats = st.as_dict()
+        _capi.check(rc)
         return dist, lab
 
     def search_device(self, d_queries: int, Q: int, K: int, ef_search: int, num_initializations: int, d_out_dist: int,

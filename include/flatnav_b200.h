@@ -121,6 +121,20 @@ int fnb_search_device(fnb_index* index, int replica, const void* d_queries, int6
  * semantics: top-K by (distance, node id), distances in the same arithmetic as fnb_search.  HOST buffers. */
 int fnb_bruteforce(fnb_index* index, const void* queries, int64_t Q, int K, float* out_dist, int32_t* out_label);
 
+/* What the last fnb_bruteforce call on this thread did.  Large problems run as a tcgen05 (tensor-core) GEMM
+ * over bf16 hi/lo splits of the vectors that only FILTERS candidates, followed by an exact re-rank in the
+ * search kernel's arithmetic; a query whose candidate list cannot be proven complete is re-scanned exactly, so
+ * the result is always the exact top-K by (distance, node id).  No reference equivalent (extension). */
+typedef struct fnb_bf_stats {
+  int32_t path;          /* 0 = CUDA-core exact scan, 1 = tensor-core filter + exact re-rank */
+  int32_t reserved;
+  int64_t n_unsafe;      /* queries re-scanned exactly because the filter margin could not be proven */
+  int64_t n_candidates;  /* candidates re-ranked exactly (sum over queries) */
+  float prep_ms, gemm_ms, rerank_ms, rescan_ms; /* device times of the four phases */
+  double gemm_flops;     /* 2*Q*N*Dpad*passes issued to the tensor cores */
+} fnb_bf_stats;
+int fnb_bruteforce_stats(fnb_bf_stats* out);
+
 /* Dataset-sharded search: k-way merge of `n_lists` per-shard result lists (each [Q, K], ascending) that
  * were gathered into DEVICE buffers d_dist / d_label of shape [n_lists, Q, K]; writes the global top-K
  * ([Q, K], ties -> lower label) to d_out_*.  Enqueued on cuda_stream. */
