@@ -117,7 +117,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "r"(taddr)
       : "memory");
 }
-__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// the registers are tied to the wait so that no use of them can be scheduled before the load has landed
+__device__ __forceinline__ void tmem_wait_ld(uint32_t (&r)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]),
+                 "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]),
+                 "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
+}
 __device__ __forceinline__ void epilogue_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 // Shared-memory matrix descriptor of a K-major [rows][64 bf16] block written by TMA with 128-byte swizzle:
@@ -141,8 +150,8 @@ struct FilterParams {
 __host__ __device__ inline uint32_t smem_lists_offset(uint32_t stages, uint32_t stage_bytes) { return stages * stage_bytes; }
 
 // per-thread unsorted list of the Kp smallest scores seen so far, [k][128 threads] in shared memory
-__device__ __noinline__ void list_insert(float* ls, uint32_t* li, const uint32_t Kp, uint32_t& cnt, uint32_t& maxpos,
-                                         float& tau, const float s, const uint32_t id) {
+__device__ __forceinline__ void list_insert(float* ls, uint32_t* li, const uint32_t Kp, uint32_t& cnt, uint32_t& maxpos,
+                                            float& tau, const float s, const uint32_t id) {
   const uint32_t slot = cnt < Kp ? cnt : maxpos;
   ls[slot * 128] = s;
   li[slot * 128] = id;
@@ -150,12 +159,12 @@ __device__ __noinline__ void list_insert(float* ls, uint32_t* li, const uint32_t
   if (cnt == Kp) {  // (re)locate the largest kept score: it is the admission threshold from now on
     float m = ls[0];
     uint32_t mp = 0;
+#pragma unroll 4
     for (uint32_t k = 1; k < Kp; k++) {
       const float v = ls[k * 128];
-      if (v > m) {
-        m = v;
-        mp = k;
-      }
+      const bool g = v > m;
+      m = g ? v : m;
+      mp = g ? k : mp;
     }
     tau = m;
     maxpos = mp;
@@ -175,7 +184,8 @@ __global__ void __launch_bounds__(THREADS, 1)
   float* xn_s = reinterpret_cast<float*>(after);                   // [2][128]
   float* ls_all = xn_s + ACC_BUFS * BN;                            // [Kp][128]
   uint32_t* li_all = reinterpret_cast<uint32_t*>(ls_all + p.Kp * 128);  // [Kp][128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(li_all + p.Kp * 128);
+  float* scratch = reinterpret_cast<float*>(li_all + p.Kp * 128);       // [32][128]: one chunk of scores per thread
+  uint64_t* bars = reinterpret_cast<uint64_t*>(scratch + 32 * 128);
   uint64_t* full = bars;
   uint64_t* empty = bars + MAX_STAGES;
   uint64_t* tfull = bars + 2 * MAX_STAGES;
@@ -286,9 +296,11 @@ __global__ void __launch_bounds__(THREADS, 1)
       const bool active = qrow < p.Q;
       uint32_t cnt = 0, maxpos = 0;
       float tau = active ? __int_as_float(0x7f800000) : __int_as_float(0xff800000);
+      float xn_next = t0 < t1 ? __ldg(p.xn + (size_t)t0 * BN + t) : 0.f;
       for (uint32_t tile = t0; tile < t1; tile++) {
         float* xs = xn_s + ab * BN;
-        xs[t] = __ldg(p.xn + (size_t)tile * BN + t);
+        xs[t] = xn_next;
+        if (tile + 1 < t1) xn_next = __ldg(p.xn + (size_t)(tile + 1) * BN + t);  // in flight during this tile
         epilogue_bar_sync();
         mbar_wait(&tfull[ab], aphase);
         tc_fence_after();
@@ -296,12 +308,36 @@ __global__ void __launch_bounds__(THREADS, 1)
         for (int c = 0; c < BN / 32; c++) {
           uint32_t r[32];
           tmem_ld32(tmem_base + lane_base + ab * BN + c * 32, r);
-          tmem_wait_ld();
-          const uint32_t id0 = tile * BN + c * 32;
+          float4 xv[8];
 #pragma unroll
-          for (int j = 0; j < 32; j++) {
-            const float s = __uint_as_float(r[j]) + xs[c * 32 + j];
-            if (s < tau) list_insert(ls, li, p.Kp, cnt, maxpos, tau, s, id0 + j);
+          for (int i = 0; i < 8; i++) xv[i] = reinterpret_cast<const float4*>(xs + c * 32)[i];
+          tmem_wait_ld(r);
+          // branch-free scan of the 32 scores of this chunk; admission is rare per thread (~Kp ln(n/Kp) / n)
+          uint32_t mask = 0;
+#pragma unroll
+          for (int i = 0; i < 8; i++) {
+            const float s0 = __uint_as_float(r[4 * i + 0]) + xv[i].x, s1 = __uint_as_float(r[4 * i + 1]) + xv[i].y;
+            const float s2 = __uint_as_float(r[4 * i + 2]) + xv[i].z, s3 = __uint_as_float(r[4 * i + 3]) + xv[i].w;
+            r[4 * i + 0] = __float_as_uint(s0);
+            r[4 * i + 1] = __float_as_uint(s1);
+            r[4 * i + 2] = __float_as_uint(s2);
+            r[4 * i + 3] = __float_as_uint(s3);
+            mask |= (s0 < tau ? 1u : 0u) << (4 * i + 0);
+            mask |= (s1 < tau ? 1u : 0u) << (4 * i + 1);
+            mask |= (s2 < tau ? 1u : 0u) << (4 * i + 2);
+            mask |= (s3 < tau ? 1u : 0u) << (4 * i + 3);
+          }
+          if (mask) {  // park the chunk in shared memory so the admitted scores can be picked by position
+            float* scr = scratch + t;
+#pragma unroll
+            for (int j = 0; j < 32; j++) scr[j * 128] = __uint_as_float(r[j]);
+            const uint32_t id0 = tile * BN + c * 32;
+            do {
+              const uint32_t j = (uint32_t)__ffs(mask) - 1u;
+              mask &= mask - 1u;
+              const float sj = scr[j * 128];
+              if (sj < tau) list_insert(ls, li, p.Kp, cnt, maxpos, tau, sj, id0 + j);
+            } while (mask);
           }
         }
         tc_fence_before();
@@ -510,7 +546,7 @@ static bool make_map(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t Dp
 }
 
 static uint32_t smem_bytes(uint32_t stages, uint32_t nsplit, uint32_t Kp) {
-  return 1024u + stages * 2u * nsplit * TILE_BYTES + ACC_BUFS * BN * 4u + Kp * 128u * 8u + (2u * MAX_STAGES + 2u * ACC_BUFS) * 8u + 16u;
+  return 1024u + stages * 2u * nsplit * TILE_BYTES + ACC_BUFS * BN * 4u + Kp * 128u * 8u + 32u * 128u * 4u + (2u * MAX_STAGES + 2u * ACC_BUFS) * 8u + 16u;
 }
 
 }  // namespace tc
