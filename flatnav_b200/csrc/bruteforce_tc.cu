@@ -171,7 +171,26 @@ __device__ __forceinline__ void list_insert(float* ls, uint32_t* li, const uint3
   }
 }
 
-template <int NSPLIT>
+// Kp == KREG: the list lives in registers, sorted ascending (+inf = empty): find the position with KREG
+// independent compares, shift with static selects.  No shared-memory latency on the (divergent) admission path.
+template <int KREG>
+__device__ __forceinline__ void reg_insert(float (&rs)[KREG], uint32_t (&ri)[KREG], float& tau, const uint32_t Kp,
+                                           const float v, const uint32_t vid) {
+  uint32_t pos = 0;
+#pragma unroll
+  for (int k = 0; k < KREG; k++) pos += (rs[k] <= v) ? 1u : 0u;
+#pragma unroll
+  for (int k = KREG - 1; k >= 0; k--) {
+    const bool keep = (uint32_t)k < pos, here = (uint32_t)k == pos;
+    const float below = k > 0 ? rs[k > 0 ? k - 1 : 0] : v;
+    const uint32_t below_i = k > 0 ? ri[k > 0 ? k - 1 : 0] : vid;
+    rs[k] = keep ? rs[k] : (here ? v : below);
+    ri[k] = keep ? ri[k] : (here ? vid : below_i);
+  }
+  tau = rs[KREG - 1];  // Kp == KREG on this path: the threshold is the last register
+}
+
+template <int NSPLIT, int KREG>
 __global__ void __launch_bounds__(THREADS, 1)
     bf_tc_kernel(const __grid_constant__ CUtensorMap tm_qh, const __grid_constant__ CUtensorMap tm_ql,
                  const __grid_constant__ CUtensorMap tm_xh, const __grid_constant__ CUtensorMap tm_xl, const FilterParams p) {
@@ -296,6 +315,13 @@ __global__ void __launch_bounds__(THREADS, 1)
       const bool active = qrow < p.Q;
       uint32_t cnt = 0, maxpos = 0;
       float tau = active ? __int_as_float(0x7f800000) : __int_as_float(0xff800000);
+      float rs[KREG > 0 ? KREG : 1];
+      uint32_t ri[KREG > 0 ? KREG : 1];
+#pragma unroll
+      for (int k = 0; k < (KREG > 0 ? KREG : 1); k++) {
+        rs[k] = __int_as_float(0x7f800000);
+        ri[k] = 0xffffffffu;
+      }
       float xn_next = t0 < t1 ? __ldg(p.xn + (size_t)t0 * BN + t) : 0.f;
       for (uint32_t tile = t0; tile < t1; tile++) {
         float* xs = xn_s + ab * BN;
@@ -336,7 +362,10 @@ __global__ void __launch_bounds__(THREADS, 1)
               const uint32_t j = (uint32_t)__ffs(mask) - 1u;
               mask &= mask - 1u;
               const float sj = scr[j * 128];
-              if (sj < tau) list_insert(ls, li, p.Kp, cnt, maxpos, tau, sj, id0 + j);
+              if (sj < tau) {
+                if (KREG > 0) reg_insert<(KREG > 0 ? KREG : 1)>(rs, ri, tau, p.Kp, sj, id0 + j);
+                else list_insert(ls, li, p.Kp, cnt, maxpos, tau, sj, id0 + j);
+              }
             } while (mask);
           }
         }
@@ -348,9 +377,21 @@ __global__ void __launch_bounds__(THREADS, 1)
       }
       if (active) {
         const size_t o = ((size_t)qrow * p.S + split) * p.Kp;
-        for (uint32_t k = 0; k < cnt; k++) {
-          p.cand_s[o + k] = ls[k * 128];
-          p.cand_id[o + k] = li[k * 128];
+        if (KREG > 0) {
+          cnt = 0;
+#pragma unroll
+          for (int k = 0; k < (KREG > 0 ? KREG : 1); k++) {
+            if ((uint32_t)k < p.Kp && ri[k] != 0xffffffffu) {
+              p.cand_s[o + k] = rs[k];
+              p.cand_id[o + k] = ri[k];
+              cnt++;
+            }
+          }
+        } else {
+          for (uint32_t k = 0; k < cnt; k++) {
+            p.cand_s[o + k] = ls[k * 128];
+            p.cand_id[o + k] = li[k * 128];
+          }
         }
         p.cand_cnt[(size_t)qrow * p.S + split] = cnt;
       }
@@ -568,13 +609,26 @@ int bruteforce_tensor(fnb_index* ix, Replica& r, const void* d_queries, int64_t 
   const uint32_t nsplit = is_f32 ? 2u : 1u;
   const uint32_t Dpad = (dim + BK - 1) / BK * BK, kblocks = Dpad / BK;
   const uint32_t n_tiles = (N + BN - 1) / BN, Npad = n_tiles * BN, n_qtiles = (Q + BM - 1) / BM;
-  const uint32_t Kp = std::max(8u, (uint32_t)K + 6u);
+  const uint32_t Kp = (uint32_t)K + 6u <= 16u ? 16u : (uint32_t)K + 6u;  // 16: the register-list kernel
   uint32_t stages = MAX_STAGES;
   while (stages > 1 && smem_bytes(stages, nsplit, Kp) > 227u * 1024u) stages--;
   if (smem_bytes(stages, nsplit, Kp) > 227u * 1024u) return fail(FNB_ERR_UNSUPPORTED, "K=%d too large for the tensor path", K);
-  // work units: ~4 per SM, a slice is at least 32 tiles (4096 rows)
-  uint32_t S = (uint32_t)std::max<int64_t>(1, ((int64_t)r.num_sms * 4 + n_qtiles / 2) / n_qtiles);
-  S = std::min(S, std::max(1u, n_tiles / 32u));
+  // work units (128 queries x one slice of the rows): few and long — admissions into the per-thread lists are
+  // ~Kp ln(n / Kp) per slice of n rows, and they are the expensive (divergent) part of the epilogue — but enough
+  // to fill the SMs evenly: among the slice counts that give 1..6 units per SM pick the best wave efficiency.
+  uint32_t S = 1;
+  {
+    const uint32_t sms = (uint32_t)r.num_sms, s_max = std::max(1u, n_tiles / 32u);
+    double best = -1.0;
+    for (uint32_t c = 1; c <= s_max && (uint64_t)c * n_qtiles <= 6ull * sms + n_qtiles; c++) {
+      const uint64_t units = (uint64_t)c * n_qtiles;
+      const double eff = (double)units / (double)(((units + sms - 1) / sms) * sms);
+      if (eff > best + 0.03) {
+        best = eff;
+        S = c;
+      }
+    }
+  }
   if (const char* e = getenv("FNB_BF_SPLITS")) S = std::max(1, atoi(e));
   S = std::min(S, n_tiles);
   const uint32_t tps = (n_tiles + S - 1) / S;
@@ -676,13 +730,20 @@ int bruteforce_tensor(fnb_index* ix, Replica& r, const void* d_queries, int64_t 
   fp.n_units = n_units;
   const uint32_t smem = smem_bytes(stages, nsplit, Kp);
   const uint32_t grid = std::min<uint32_t>(n_units, (uint32_t)r.num_sms);
+  const bool reglist = Kp == 16 && !getenv("FNB_BF_SMEM_LIST");
+#define TC_LAUNCH(NS, KR)                                                                                       \
+  do {                                                                                                          \
+    TC_CU(cudaFuncSetAttribute(bf_tc_kernel<NS, KR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    bf_tc_kernel<NS, KR><<<grid, THREADS, smem, s>>>(m_qh, m_ql, m_xh, m_xl, fp);                               \
+  } while (0)
   if (nsplit == 2) {
-    TC_CU(cudaFuncSetAttribute(bf_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    bf_tc_kernel<2><<<grid, THREADS, smem, s>>>(m_qh, m_ql, m_xh, m_xl, fp);
+    if (reglist) TC_LAUNCH(2, 16);
+    else TC_LAUNCH(2, 0);
   } else {
-    TC_CU(cudaFuncSetAttribute(bf_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    bf_tc_kernel<1><<<grid, THREADS, smem, s>>>(m_qh, m_ql, m_xh, m_xl, fp);
+    if (reglist) TC_LAUNCH(1, 16);
+    else TC_LAUNCH(1, 0);
   }
+#undef TC_LAUNCH
   TC_CU(cudaGetLastError());
   TC_CU(cudaEventRecord(ev[2], s));
 
