@@ -132,6 +132,16 @@ static int parse_header(const unsigned char* p, size_t nbytes, int metric, int e
   return FNB_OK;
 }
 
+// Row pitch of the vector array in 16-byte chunks.  FNB_ROW_ALIGN (chunks, power of two) overrides the layout rule
+// of fnb_layout.h for experiments.
+static uint32_t row_stride_chunks(uint32_t nchunks) {
+  if (const char* e = getenv("FNB_ROW_ALIGN")) {
+    const uint32_t a = (uint32_t)atoi(e);
+    if (a >= 1 && a <= 64 && (a & (a - 1)) == 0) return (nchunks + a - 1) & ~(a - 1);
+  }
+  return fnb_stride_chunks(nchunks);
+}
+
 static int upload_replica(const Header& h, const unsigned char* blob, int device, Replica* r) {
   CU(cudaSetDevice(device));
   r->device = device;
@@ -142,7 +152,7 @@ static int upload_replica(const Header& h, const unsigned char* blob, int device
                 prop.major, prop.minor);
   r->num_sms = prop.multiProcessorCount;
   const uint32_t nchunks = fnb_nchunks(h.data_size);
-  const uint32_t stride = fnb_stride_chunks(nchunks);
+  const uint32_t stride = row_stride_chunks(nchunks);
   const uint64_t n = h.cur_nodes ? h.cur_nodes : 1;
   const uint64_t blob_bytes = h.node_size * h.cur_nodes;
   unsigned char* d_blob = nullptr;
@@ -222,7 +232,7 @@ static int build_index(const unsigned char* file, size_t nbytes, int metric, int
   fnb_index* ix = new fnb_index();
   ix->h = h;
   ix->nchunks = fnb_nchunks(h.data_size);
-  ix->stride = fnb_stride_chunks(ix->nchunks);
+  ix->stride = row_stride_chunks(ix->nchunks);
   ix->G = fnb_lanes_per_row(ix->nchunks);
   ix->replicas.resize(devs.size());
   for (size_t i = 0; i < devs.size(); i++) {

@@ -16,16 +16,18 @@ if ROOT not in sys.path:
 CACHE = os.environ.get("FNB_DATA_CACHE", os.path.join(ROOT, "data_cache"))
 
 
-def index_name(gen: str, n: int, dim: int, metric: str, M: int, efc: int) -> str:
-    return f"{gen}_n{n}_d{dim}_{metric}_M{M}_efc{efc}_seed42"
+def index_name(gen: str, n: int, dim: int, metric: str, M: int, efc: int, rank: int = 16) -> str:
+    r = "" if rank == 16 else f"_r{rank}"
+    return f"{gen}{r}_n{n}_d{dim}_{metric}_M{M}_efc{efc}_seed42"
 
 
-def ensure_index(gen: str, n: int, dim: int, metric: str, M: int = 32, efc: int = 100, threads: int = 0):
+def ensure_index(gen: str, n: int, dim: int, metric: str, M: int = 32, efc: int = 100, threads: int = 0,
+                 rank: int = 16):
     """Return (path, info).  Builds with the reference binary if the file is not cached."""
     from flatnav_b200 import synthetic
     from oracle import refbin
     os.makedirs(CACHE, exist_ok=True)
-    path = os.path.join(CACHE, index_name(gen, n, dim, metric, M, efc) + ".idx")
+    path = os.path.join(CACHE, index_name(gen, n, dim, metric, M, efc, rank) + ".idx")
     meta = path + ".json"
     if os.path.exists(path) and os.path.exists(meta):
         info = json.load(open(meta))
@@ -34,7 +36,7 @@ def ensure_index(gen: str, n: int, dim: int, metric: str, M: int = 32, efc: int 
     if not refbin.available():
         raise RuntimeError("no cached index and the reference builder (oracle/_ref) cannot run on this host")
     t0 = time.time()
-    data = synthetic.make(gen, n, dim)
+    data = synthetic.make(gen, n, dim, rank=rank)
     t_gen = time.time() - t0
     info = refbin.build_index(data, metric, M, efc, path + ".tmp", threads=threads or (os.cpu_count() or 1))
     os.replace(path + ".tmp", path)
