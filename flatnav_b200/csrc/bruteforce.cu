@@ -97,7 +97,11 @@ static cudaError_t launch_bf(const BfParams& p, cudaStream_t s) {
 
 template <int DT, int METRIC>
 static cudaError_t bf_gc(const fnb_index* ix, const BfParams& p, cudaStream_t s) {
-  const int ch = fnb_chunks_per_lane(ix->nchunks);
+  const int ch = fnb_chunks_per_lane(ix->nchunks, ix->G);
+  if (ix->G == 4) {
+    if (ch <= 1) return launch_bf<DT, METRIC, 4, 1>(p, s);
+    return launch_bf<DT, METRIC, 4, 2>(p, s);
+  }
   if (ix->G == 8) {
     switch (ch) {
       case 1: return launch_bf<DT, METRIC, 8, 1>(p, s);

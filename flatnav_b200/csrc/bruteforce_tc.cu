@@ -533,7 +533,11 @@ static cudaError_t launch_rerank(const RerankParams& p, uint32_t nchunks, cudaSt
 }
 template <int DT, int METRIC>
 static cudaError_t rerank_gc(const fnb_index* ix, const RerankParams& p, cudaStream_t s) {
-  const int ch = fnb_chunks_per_lane(ix->nchunks);
+  const int ch = fnb_chunks_per_lane(ix->nchunks, ix->G);
+  if (ix->G == 4) {
+    if (ch <= 1) return launch_rerank<DT, METRIC, 4, 1>(p, ix->nchunks, s);
+    return launch_rerank<DT, METRIC, 4, 2>(p, ix->nchunks, s);
+  }
   if (ix->G == 8) {
     switch (ch) {
       case 1: return launch_rerank<DT, METRIC, 8, 1>(p, ix->nchunks, s);

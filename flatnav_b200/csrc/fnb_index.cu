@@ -233,7 +233,7 @@ static int build_index(const unsigned char* file, size_t nbytes, int metric, int
   ix->h = h;
   ix->nchunks = fnb_nchunks(h.data_size);
   ix->stride = row_stride_chunks(ix->nchunks);
-  ix->G = fnb_lanes_per_row(ix->nchunks);
+  ix->G = fnb_lanes_per_row(ix->nchunks, h.data_type != FNB_DTYPE_FLOAT32 && !getenv("FNB_NO_G4"));
   ix->replicas.resize(devs.size());
   for (size_t i = 0; i < devs.size(); i++) {
     rc = upload_replica(h, file + FNB_HEADER_BYTES, devs[i], &ix->replicas[i]);
@@ -278,7 +278,7 @@ int plan_search(const fnb_index* ix, int64_t Q, int K, int ef, int ninit, Search
   while (p->Bpow2 * 2u <= p->Bcap) p->Bpow2 *= 2u;
   p->lines_per_row = (ix->stride * FNB_CHUNK_BYTES + 127u) / 128u;
   const char* env = getenv("FNB_VS_BUCKETS");  // development / test knob: visited-set buckets per query
-  size_visited(*p, env ? atoi(env) : 0, fnb_min_ctas(fnb_chunks_per_lane(ix->nchunks)));
+  size_visited(*p, env ? atoi(env) : 0, fnb_min_ctas(fnb_chunks_per_lane(ix->nchunks, ix->G)));
   if ((uint64_t)p->warp_smem * FNB_WARPS_PER_CTA > 227u * 1024u)
     return fail(FNB_ERR_UNSUPPORTED, "ef_search=%d needs %u bytes of shared memory per query; limit is %u", ef,
                 p->warp_smem, 227u * 1024u / FNB_WARPS_PER_CTA);

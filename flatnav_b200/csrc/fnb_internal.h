@@ -61,7 +61,11 @@ cudaError_t dispatch_search_i8(const fnb_index* ix, const SearchParams& p, int n
 
 template <int DT, int METRIC>
 static inline cudaError_t dispatch_gc(const fnb_index* ix, const SearchParams& p, int num_sms, cudaStream_t s) {
-  const int ch = fnb_chunks_per_lane(ix->nchunks);
+  const int ch = fnb_chunks_per_lane(ix->nchunks, ix->G);
+  if (ix->G == 4) {
+    if (ch <= 1) return launch_search<DT, METRIC, 4, 1>(p, num_sms, s);
+    return launch_search<DT, METRIC, 4, 2>(p, num_sms, s);
+  }
   if (ix->G == 8) {
     switch (ch) {
       case 1: return launch_search<DT, METRIC, 8, 1>(p, num_sms, s);

@@ -47,7 +47,12 @@ enum { M_L2 = 0, M_IP = 1 };
 #ifndef FNB_CTAS_SHORT_ROWS
 #define FNB_CTAS_SHORT_ROWS 6
 #endif
-__host__ __device__ constexpr int fnb_min_ctas(int ch) { return ch <= 4 ? FNB_CTAS_SHORT_ROWS : (ch <= 8 ? 4 : 3); }
+#ifndef FNB_CTAS_TINY_ROWS
+#define FNB_CTAS_TINY_ROWS FNB_CTAS_SHORT_ROWS
+#endif
+__host__ __device__ constexpr int fnb_min_ctas(int ch) {
+  return ch <= 1 ? FNB_CTAS_TINY_ROWS : (ch <= 4 ? FNB_CTAS_SHORT_ROWS : (ch <= 8 ? 4 : 3));
+}
 __host__ __device__ constexpr int fnb_batches_in_flight(int ch) { return ch >= 4 ? 1 : 4 / ch; }
 #define FNB_FULL 0xffffffffu
 #define FNB_EMPTY 0xffffffffu
