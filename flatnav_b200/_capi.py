@@ -15,6 +15,7 @@ FNB_OK, FNB_SHORT_RESULT = 0, 1
 FNB_ERR_INVALID_ARG, FNB_ERR_IO, FNB_ERR_FORMAT, FNB_ERR_CUDA, FNB_ERR_UNSUPPORTED, FNB_ERR_NOMEM = -1, -2, -3, -4, -5, -6
 FNB_DTYPE_UINT8, FNB_DTYPE_INT8, FNB_DTYPE_FLOAT32, FNB_DTYPE_ANY = 0, 4, 9, -1
 FNB_METRIC_L2, FNB_METRIC_IP = 0, 1
+FNB_IPC_HANDLE_BYTES = 64
 
 
 class FnbInfo(C.Structure):
@@ -67,6 +68,13 @@ EXPORTS = {
     "fnb_bruteforce_stats": (C.c_int, [C.POINTER(FnbBfStats)]),
     "fnb_merge_topk": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_void_p, C.c_void_p,
                                  C.c_void_p]),
+    "fnb_exchange_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int, C.POINTER(C.c_void_p)]),
+    "fnb_exchange_handle": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "fnb_exchange_attach": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "fnb_search_sharded": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int,
+                                     C.c_void_p, C.c_void_p, C.c_void_p]),
+    "fnb_exchange_status": (C.c_int, [C.c_void_p]),
+    "fnb_exchange_free": (None, [C.c_void_p]),
     "fnb_last_error": (C.c_char_p, []),
     "fnb_version": (C.c_char_p, []),
 }

@@ -8,9 +8,12 @@ multi-process or multi-device mode.  Two modes here:
                      No collective on the data path; `gather_results` is only for callers that want the whole
                      result on every rank.
 * dataset sharding — every rank holds ONE sub-graph built over a contiguous id range whose labels are global ids;
-                     every rank searches ALL queries on its shard, the per-shard `(dist, label)[Q, K]` lists are
-                     all-gathered (NCCL over NVLink) and merged on the device by `fnb_merge_topk`
-                     (ties -> lower label).
+                     every rank searches ALL queries on its shard and the per-shard `(dist, label)[Q, K]` lists are
+                     combined into the global top-K (ties -> lower label).  Two exchange paths:
+                       "peer"  (default on GPUs) `fnb_search_sharded`: after the traversal ONE kernel pushes the lists
+                               into every peer's gather buffer through CUDA-IPC peer pointers over NVLink, signals /
+                               awaits per-rank flags and merges — no collective call on the data path;
+                       "nccl"  the baseline: `all_gather_into_tensor` + `fnb_merge_topk`.
 
 The search and merge steps are injectable so the host logic (partitioning, gather layout, merge order) is covered
 by world_size-2 `gloo` tests on CPU with the oracle standing in for the CUDA kernels (tests only).
@@ -88,11 +91,89 @@ class DatasetShardedSearcher:
     """One sub-graph per rank (labels are global ids); all ranks answer all queries; all-gather + k-way merge."""
 
     def __init__(self, shard_index, group=None,
-                 search_fn: Optional[Callable] = None, merge_fn: Optional[Callable] = None):
+                 search_fn: Optional[Callable] = None, merge_fn: Optional[Callable] = None,
+                 exchange: str = "peer", max_queries: int = 1 << 17, max_k: int = 128):
         self.index = shard_index
         self.group = group
         self._search_fn = search_fn
         self._merge_fn = merge_fn or merge_topk_cuda
+        self.exchange = "nccl" if search_fn is not None else exchange
+        self._ex = None
+        self._cap = (int(max_queries), int(max_k))
+
+    # ---- "peer" path: gather buffers in NVLink peer memory, set up once -----------------------------------
+    def _peer_exchange(self):
+        if self._ex is not None:
+            return self._ex
+        import ctypes as C
+
+        import torch
+
+        from . import _capi
+        dist = _dist()
+        world, rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        ex = C.c_void_p()
+        _capi.check(_capi.lib().fnb_exchange_create(torch.cuda.current_device(), rank, world, self._cap[0], self._cap[1],
+                                                    C.byref(ex)))
+        mine = C.create_string_buffer(_capi.FNB_IPC_HANDLE_BYTES)
+        _capi.check(_capi.lib().fnb_exchange_handle(ex, mine))
+        handles = [None] * world
+        dist.all_gather_object(handles, bytes(mine.raw), group=self.group)  # control plane only
+        blob = C.create_string_buffer(b"".join(handles), world * _capi.FNB_IPC_HANDLE_BYTES)
+        _capi.check(_capi.lib().fnb_exchange_attach(ex, blob))
+        dist.barrier(group=self.group)
+        self._ex = ex
+        return ex
+
+    def close(self):
+        if self._ex is not None:
+            from . import _capi
+            _dist().barrier(group=self.group)  # nobody may still be pushing into a buffer that is about to go
+            _capi.lib().fnb_exchange_free(self._ex)
+            self._ex = None
+
+    def search_device(self, d_queries: int, Q: int, K: int, ef_search: int, num_initializations: int, d_out_dist: int,
+                      d_out_label: int, stream: int = 0) -> None:
+        """Collective, asynchronous: raw device pointers in, global top-K [Q, K] out (peer-memory path)."""
+        from . import _capi
+        _capi.check(_capi.lib().fnb_search_sharded(self.index._h, self._peer_exchange(), d_queries, Q, K, ef_search,
+                                                   num_initializations, d_out_dist, d_out_label, stream or None))
+
+    def search_tensors(self, dq, K: int, ef_search: int, num_initializations: int = 100):
+        """Collective and asynchronous on the current stream: `dq` is a CUDA tensor [Q, dim] of the index dtype;
+        returns CUDA tensors (float32 [Q, K], int32 [Q, K]) with the global top-K.  Used by the benchmarks."""
+        import torch
+        Q = dq.shape[0]
+        stream = torch.cuda.current_stream().cuda_stream
+        od = torch.empty((Q, K), dtype=torch.float32, device=dq.device)
+        ol = torch.empty((Q, K), dtype=torch.int32, device=dq.device)
+        if self.exchange == "peer":
+            self.search_device(dq.data_ptr(), Q, K, ef_search, num_initializations, od.data_ptr(), ol.data_ptr(), stream)
+            return od, ol
+        dist = _dist()
+        world = dist.get_world_size(self.group)
+        d = torch.empty((Q, K), dtype=torch.float32, device=dq.device)
+        l = torch.empty((Q, K), dtype=torch.int32, device=dq.device)
+        self.index.search_device(dq.data_ptr(), Q, K, ef_search, num_initializations, d.data_ptr(), l.data_ptr(), stream)
+        gd = torch.empty((world * Q, K), dtype=d.dtype, device=d.device)
+        gl = torch.empty((world * Q, K), dtype=l.dtype, device=l.device)
+        dist.all_gather_into_tensor(gd, d, group=self.group)
+        dist.all_gather_into_tensor(gl, l, group=self.group)
+        return merge_topk_cuda(gd.view(world, Q, K), gl.view(world, Q, K), K)
+
+    def _search_peer(self, queries, K, ef, ninit):
+        import torch
+
+        from . import _capi
+        Q = queries.shape[0]
+        dq = torch.from_numpy(np.ascontiguousarray(queries)).cuda()
+        od = torch.empty((Q, K), dtype=torch.float32, device="cuda")
+        ol = torch.empty((Q, K), dtype=torch.int32, device="cuda")
+        self.search_device(dq.data_ptr(), Q, K, ef, ninit, od.data_ptr(), ol.data_ptr(),
+                           torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        _capi.check(_capi.lib().fnb_exchange_status(self._ex))
+        return od.cpu().numpy(), ol.cpu().numpy()
 
     def _local(self, queries, K, ef, ninit):
         import torch
@@ -111,6 +192,8 @@ class DatasetShardedSearcher:
         import torch
         dist = _dist()
         world = dist.get_world_size(self.group)
+        if self.exchange == "peer":
+            return self._search_peer(queries, K, ef_search, num_initializations)
         d, l = self._local(queries, K, ef_search, num_initializations)
         Q = d.shape[0]
         gd = torch.empty((world * Q, K), dtype=d.dtype, device=d.device)  # rank-major concatenation

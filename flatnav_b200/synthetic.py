@@ -40,11 +40,13 @@ def _draw(gen: str, n: int, dim: int, seed: int, rank: int, sigma: float, chunk:
     return out
 
 
-def make(gen: str, n: int, dim: int, *, queries: bool = False, rank: int = 16, sigma: float = 0.1) -> np.ndarray:
-    """Return `n` vectors of generator `gen` (database stream, or the query stream if `queries`)."""
+def make(gen: str, n: int, dim: int, *, queries: bool = False, rank: int = 16, sigma: float = 0.1,
+         stream: int = 0) -> np.ndarray:
+    """Return `n` vectors of generator `gen` (database stream, or the query stream if `queries`).
+    `stream` > 0 selects an independent draw of the same law (dataset shards)."""
     if gen not in GENERATORS:
         raise ValueError(f"unknown generator {gen!r}; expected one of {GENERATORS}")
-    seed = QUERY_SEED if queries else DATA_SEED
+    seed = (QUERY_SEED if queries else DATA_SEED) + 7919 * stream
     base = "iid" if gen == "iid" else "latent"
     x = _draw(base, n, dim, seed, rank, sigma)
     if gen == "latent-norm":

@@ -141,6 +141,25 @@ int fnb_bruteforce_stats(fnb_bf_stats* out);
 int fnb_merge_topk(const float* d_dist, const int32_t* d_label, int n_lists, int64_t Q, int K, float* d_out_dist,
                    int32_t* d_out_label, void* cuda_stream);
 
+/* ---- dataset-sharded search over NVLink peer memory (one process per GPU) ------------------------------ */
+/* The reference has no multi-device mode (its only parallelism is executeInParallel over queries,
+ * include/flatnav/util/Multithreading.h:18-48).  Every rank holds one sub-graph (labels = global ids), answers all
+ * queries on it, and the per-shard top-K lists are merged.  fnb_search_sharded does the exchange without a
+ * collective library: after the local traversal ONE kernel pushes this rank's lists into every peer's gather
+ * buffer through CUDA-IPC-mapped pointers, publishes / awaits per-rank epoch flags and runs the k-way merge
+ * (ties -> lower label).  Usage: create on every rank, exchange the 64-byte handles out of band (e.g.
+ * torch.distributed.all_gather_object), attach, then call fnb_search_sharded collectively (same Q, K everywhere). */
+#define FNB_IPC_HANDLE_BYTES 64
+typedef struct fnb_exchange fnb_exchange;
+int fnb_exchange_create(int device, int rank, int world, int64_t max_Q, int max_K, fnb_exchange** out);
+int fnb_exchange_handle(fnb_exchange* ex, void* handle_out /* FNB_IPC_HANDLE_BYTES */);
+int fnb_exchange_attach(fnb_exchange* ex, const void* handles /* world x FNB_IPC_HANDLE_BYTES, rank order */);
+/* DEVICE buffers; enqueued on cuda_stream, not synchronised.  d_out_* receive the global top-K [Q, K]. */
+int fnb_search_sharded(fnb_index* shard, fnb_exchange* ex, const void* d_queries, int64_t Q, int K, int ef_search,
+                       int num_initializations, float* d_out_dist, int32_t* d_out_label, void* cuda_stream);
+int fnb_exchange_status(fnb_exchange* ex); /* after a synchronise: FNB_ERR_CUDA if a peer never delivered */
+void fnb_exchange_free(fnb_exchange* ex);
+
 const char* fnb_last_error(void);
 const char* fnb_version(void);
 

@@ -67,7 +67,7 @@ static std::vector<char> read_file(const std::string& path, size_t expect_bytes)
 }
 
 template <typename dist_t, typename elem_t>
-static int do_build(DataType dt, char** a) {
+static int do_build(DataType dt, char** a, int nargs) {
   std::string data_path = a[0];
   size_t N = std::strtoull(a[1], nullptr, 10), D = std::strtoull(a[2], nullptr, 10);
   int M = std::atoi(a[3]), efc = std::atoi(a[4]), threads = std::atoi(a[5]);
@@ -77,7 +77,7 @@ static int do_build(DataType dt, char** a) {
   auto index = std::make_unique<Index<dist_t, int>>(std::move(dist), (int)N, M, /*collect_stats=*/false, dt);
   index->setNumThreads((uint32_t)threads);
   std::vector<int> labels(N);
-  std::iota(labels.begin(), labels.end(), 0);
+  std::iota(labels.begin(), labels.end(), nargs > 7 ? std::atoi(a[7]) : 0);  // optional first label (dataset shards)
   auto t0 = std::chrono::steady_clock::now();
   index->template addBatch<elem_t>((void*)data.data(), labels, efc);
   double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
@@ -158,7 +158,7 @@ static int do_info(char** a) {
 
 template <typename dist_t, typename elem_t>
 static int run(const std::string& op, DataType dt, char** a, int n) {
-  if (op == "build" && n >= 7) return do_build<dist_t, elem_t>(dt, a);
+  if (op == "build" && n >= 7) return do_build<dist_t, elem_t>(dt, a, n);
   if (op == "search" && n >= 9) return do_search<dist_t, elem_t>(a, n);
   if (op == "info" && n >= 1) return do_info<dist_t>(a);
   std::fprintf(stderr, "bad arguments for %s\n", op.c_str());

@@ -61,14 +61,15 @@ def _run(args: list[str], timeout: float | None = None) -> dict:
 
 
 def build_index(data: np.ndarray, metric: str, M: int, ef_construction: int, out_path: str, threads: int = 0,
-                timeout: float | None = None) -> dict:
-    """Index::addBatch + saveIndex with the reference itself.  `metric` is "l2" or "ip"."""
+                timeout: float | None = None, first_label: int = 0) -> dict:
+    """Index::addBatch + saveIndex with the reference itself.  `metric` is "l2" or "ip".  Labels are
+    first_label, first_label + 1, ... in row order (dataset shards carry global ids)."""
     data = np.ascontiguousarray(data)
     threads = threads or (os.cpu_count() or 1)
     with tempfile.NamedTemporaryFile(suffix=".bin", dir=os.path.dirname(os.path.abspath(out_path))) as f:
         data.tofile(f.name)
         return _run(["build", metric, DT[data.dtype], f.name, str(data.shape[0]), str(data.shape[1]), str(M),
-                     str(ef_construction), str(threads), out_path], timeout=timeout)
+                     str(ef_construction), str(threads), out_path, str(first_label)], timeout=timeout)
 
 
 def search(index_path: str, metric: str, queries: np.ndarray, K: int, ef: int, ninit: int = 100, threads: int = 1,

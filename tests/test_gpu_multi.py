@@ -58,9 +58,16 @@ def _worker(rank, world, port_no, out_dir, shard_paths):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     q = np.load(os.path.join(ROOT, "tests", "golden", "l2_f32_d24.npz"))["queries"]
     ix = flatnav_b200.index.IndexL2Float.load_index(shard_paths[rank], devices=[rank])
-    d, l = DatasetShardedSearcher(ix).search(q, 10, 50)
-    np.save(os.path.join(out_dir, f"d_{rank}.npy"), d)
-    np.save(os.path.join(out_dir, f"l_{rank}.npy"), l)
+    for mode in ("nccl", "peer"):
+        sh = DatasetShardedSearcher(ix, exchange=mode, max_queries=4096, max_k=16)
+        for rep in range(3):  # several epochs through the double-buffered peer exchange
+            d, l = sh.search(q, 10, 50)
+        d1, l1 = sh.search(q[:7], 3, 20)  # a different (Q, K) through the same buffers
+        np.save(os.path.join(out_dir, f"d_{mode}_{rank}.npy"), d)
+        np.save(os.path.join(out_dir, f"l_{mode}_{rank}.npy"), l)
+        np.save(os.path.join(out_dir, f"d1_{mode}_{rank}.npy"), d1)
+        np.save(os.path.join(out_dir, f"l1_{mode}_{rank}.npy"), l1)
+        sh.close()
     dist.destroy_process_group()
 
 
@@ -92,6 +99,9 @@ def test_dataset_sharding_over_nccl(tmp_path):
         pairs = sorted((float(per[s][0][i, k]), int(per[s][1][i, k])) for s in range(2) for k in range(10))[:10]
         exp_d[i] = [p[0] for p in pairs]
         exp_l[i] = [p[1] for p in pairs]
-    for r in range(2):
-        np.testing.assert_array_equal(np.load(tmp_path / f"d_{r}.npy"), exp_d)
-        np.testing.assert_array_equal(np.load(tmp_path / f"l_{r}.npy"), exp_l)
+    for mode in ("nccl", "peer"):
+        for r in range(2):
+            np.testing.assert_array_equal(np.load(tmp_path / f"d_{mode}_{r}.npy"), exp_d)
+            np.testing.assert_array_equal(np.load(tmp_path / f"l_{mode}_{r}.npy"), exp_l)
+            np.testing.assert_array_equal(np.load(tmp_path / f"d1_{mode}_{r}.npy"), np.load(tmp_path / "d1_nccl_0.npy"))
+            np.testing.assert_array_equal(np.load(tmp_path / f"l1_{mode}_{r}.npy"), np.load(tmp_path / "l1_nccl_0.npy"))
