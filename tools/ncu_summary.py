@@ -31,7 +31,10 @@ KEEP = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio",
-        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "sm__throughput.avg.pct_of_peak_sustained_elapsed"]
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
+        "sm__inst_executed_pipe_tensor_subpipe_hmma.avg.pct_of_peak_sustained_active",
+        "l1tex__m_xbar2l1tex_read_bytes_mem_global_op_tma_ld.sum", "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio"]
 
 
 def launches(tag, path):
@@ -63,12 +66,13 @@ def launches(tag, path):
             f.write(f"| {i} | `{n}` | {g} | {b} | {ms:.4f} |\n")
 
 
-def full(tag, rep):
+def full(tag, rep, name="search_kernel", traffic_json=True):
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units, vals = rows[0], rows[1], rows[2]
+    hdr0 = hdr
     got = {}
-    with open(os.path.join(OUT, f"{tag}_search_kernel_metrics.csv"), "w") as f:
+    with open(os.path.join(OUT, f"{tag}_{name}_metrics.csv"), "w") as f:
         w = csv.writer(f)
         w.writerow(["metric", "value", "unit"])
         w.writerow(["kernel", vals[hdr.index("Kernel Name")], ""])
@@ -82,9 +86,10 @@ def full(tag, rep):
         return x * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}[u]
 
     traffic = to_bytes(*got["dram__bytes_read.sum"]) + to_bytes(*got["dram__bytes_write.sum"])
-    json.dump({"dram_bytes_per_launch": traffic, "source": f"profiles/{tag}_search_kernel_metrics.csv "
-               "(dram__bytes_read.sum + dram__bytes_write.sum, one ncu --set full capture of fnb_search_kernel, "
-               "bench.py workload)"}, open(os.path.join(OUT, "roofline_traffic.json"), "w"), indent=1)
+    if traffic_json:
+        json.dump({"dram_bytes_per_launch": traffic, "source": f"profiles/{tag}_search_kernel_metrics.csv "
+                   "(dram__bytes_read.sum + dram__bytes_write.sum, one ncu --set full capture of fnb_search_kernel, "
+                   "bench.py workload)"}, open(os.path.join(OUT, "roofline_traffic.json"), "w"), indent=1)
     src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--print-source", "cuda,sass", "--csv"],
                          capture_output=True, text=True).stdout
     rows = list(csv.reader(src.splitlines()))
@@ -99,10 +104,10 @@ def full(tag, rep):
             except ValueError:
                 pass
     ti, ts = sum(x[2] for x in lines) or 1, sum(x[3] for x in lines) or 1
-    with open(os.path.join(OUT, f"{tag}_search_kernel_hotlines.md"), "w") as f:
-        f.write(f"# {tag}: hottest source lines of fnb_search_kernel (ncu --set full --import-source on; -lineinfo)\n\n"
+    with open(os.path.join(OUT, f"{tag}_{name}_hotlines.md"), "w") as f:
+        f.write(f"# {tag}: hottest source lines of {vals[hdr0.index('Kernel Name')][:90]} (ncu --set full --import-source on; -lineinfo)\n\n"
                 f"total warp-instructions attributed: {ti}, stall samples: {ts}\n\n"
-                "| line (search_kernel.cuh) | % instructions | % stall samples | source |\n|---:|---:|---:|---|\n")
+                "| line | % instructions | % stall samples | source |\n|---:|---:|---:|---|\n")
         for ln, s, i, sa in sorted(lines, key=lambda x: -x[2])[:30]:
             f.write(f"| {ln} | {100 * i / ti:.1f} | {100 * sa / ts:.1f} | `{s[:110]}` |\n")
 
@@ -110,6 +115,8 @@ def full(tag, rep):
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     tag = sys.argv[1]
-    launches(tag, sys.argv[2])
-    full(tag, sys.argv[3])
+    name = sys.argv[sys.argv.index("--name") + 1] if "--name" in sys.argv else "search_kernel"
+    if sys.argv[2] != "-":
+        launches(tag, sys.argv[2])
+    full(tag, sys.argv[3], name=name, traffic_json="--no-traffic" not in sys.argv)
     print("wrote profiles for", tag)
