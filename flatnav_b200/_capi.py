@@ -39,6 +39,14 @@ class FnbSearchStats(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
 
 
+class FnbBuildStats(C.Structure):
+    _fields_ = [("n_added", C.c_int64), ("n_batches", C.c_int64), ("n_dropped_backlinks", C.c_int64),
+                ("device_ms", C.c_float), ("reserved", C.c_float)]
+
+    def as_dict(self) -> dict:
+        return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+
+
 class FnbBfStats(C.Structure):
     _fields_ = [
         ("path", C.c_int32), ("reserved", C.c_int32), ("n_unsafe", C.c_int64), ("n_candidates", C.c_int64),
@@ -55,6 +63,10 @@ EXPORTS = {
     "fnb_index_load": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_void_p)]),
     "fnb_index_from_memory": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int,
                                         C.POINTER(C.c_void_p)]),
+    "fnb_index_create": (C.c_int, [C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.POINTER(C.c_void_p)]),
+    "fnb_index_reserve": (C.c_int, [C.c_void_p, C.c_uint64]),
+    "fnb_index_add": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int,
+                                C.POINTER(FnbBuildStats)]),
     "fnb_index_save": (C.c_int, [C.c_void_p, C.c_char_p]),
     "fnb_index_info": (C.c_int, [C.c_void_p, C.POINTER(FnbInfo)]),
     "fnb_index_free": (None, [C.c_void_p]),

@@ -35,6 +35,7 @@ __global__ void __launch_bounds__(BF_WARPS * 32) bruteforce_kernel(const BfParam
   sp.dim = p.dim;
   sp.nchunks = p.nchunks;
   sp.query_vec_ok = p.query_vec_ok;
+  sp.query_pitch_chunks = 0;
   uint4 q[CH];
 #pragma unroll
   for (int k = 0; k < CH; k++) q[k] = active ? load_query_chunk<DT>(sp, qi, (uint32_t)(k * G + pos)) : make_uint4(0, 0, 0, 0);

@@ -168,6 +168,7 @@ static int upload_replica(const Header& h, const unsigned char* blob, int device
   CU(cudaEventCreate(&r->ev[2]));
   CU(cudaEventCreate(&r->ev[3]));
   r->device_bytes = n * stride * FNB_CHUNK_BYTES + n * h.M * 4 + n * 4;
+  r->capacity = n;
   if (h.cur_nodes) {
     CU(cudaMalloc(&d_blob, blob_bytes));
     CU(cudaMemcpy(d_blob, blob, blob_bytes, cudaMemcpyHostToDevice));

@@ -37,6 +37,7 @@ struct Replica {
   unsigned char* h_pinned = nullptr;
   size_t h_pinned_bytes = 0;
   uint64_t device_bytes = 0;
+  uint64_t capacity = 0;  // rows the vec / adj / labels arrays can hold (>= cur_nodes; construction grows it)
 };
 
 int fail(int code, const char* fmt, ...);

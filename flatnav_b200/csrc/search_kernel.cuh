@@ -78,6 +78,8 @@ struct SearchParams {
   uint32_t lines_per_row;  // 128-byte lines per padded row (for the L2 prefetch)
   uint32_t warp_smem;  // bytes of shared memory per warp
   uint32_t query_vec_ok;  // 1 => query rows are 16-byte aligned and a whole number of chunks
+  uint32_t query_pitch_chunks;  // != 0 => queries are rows of a padded vector array with this pitch (construction:
+                                // the new nodes' own rows); chunks beyond the data are zero there
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -202,6 +204,7 @@ template <int DT>
 __device__ __forceinline__ uint4 load_query_chunk(const SearchParams& p, uint32_t qi, uint32_t chunk) {
   uint4 r = make_uint4(0, 0, 0, 0);
   if (chunk >= p.nchunks) return r;
+  if (p.query_pitch_chunks) return __ldg(reinterpret_cast<const uint4*>(p.queries) + (size_t)qi * p.query_pitch_chunks + chunk);
   if (p.query_vec_ok) {
     const uint4* row = reinterpret_cast<const uint4*>(p.queries) + (size_t)qi * p.nchunks;
     return __ldg(row + chunk);
@@ -528,7 +531,7 @@ __global__ void __launch_bounds__(FNB_WARPS_PER_CTA * 32, fnb_min_ctas(CH)) fnb_
       if (i < len) {
         const uint64_t e = list[i];
         od = unord_f32((uint32_t)(e >> 32));
-        ol = __ldg(p.labels + ((uint32_t)e >> 1));
+        ol = p.labels ? __ldg(p.labels + ((uint32_t)e >> 1)) : (int32_t)((uint32_t)e >> 1);  // null: node ids
       }
       p.out_dist[(size_t)qi * p.K + i] = od;
       p.out_label[(size_t)qi * p.K + i] = ol;

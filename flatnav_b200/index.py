@@ -3,9 +3,9 @@
 Mirrors the classes `IndexL2Float / IndexL2Uint8 / IndexL2Int8 / IndexIPFloat / IndexIPUint8 / IndexIPInt8`
 bound in python-bindings/src/flatnav/bindings.cpp:358-395, 426-474 of the reference: same method names,
 argument meaning, return dtypes/shapes and exception types for `load_index`, `search`, `search_single`,
-`save`, `set_num_threads`, `num_threads`, `max_edges_per_node`, `get_query_distance_computations`.
-Construction-side methods (`add`, `allocate_nodes`, `build_graph_links`, `reorder`, `create`) are outside
-the hot path this package replaces: build the index with the reference and load it here.
+`save`, `set_num_threads`, `num_threads`, `max_edges_per_node`, `get_query_distance_computations`, and — the caller
+side of the search path, SURVEY.md §8f — `create` / `add` (GPU batched construction, csrc/build.cu).
+`allocate_nodes`, `build_graph_links` and `reorder` stay with the reference: build or reorder there, load here.
 """
 from __future__ import annotations
 
@@ -18,8 +18,8 @@ from . import _capi
 from .data_type import DataType
 
 _NP = {DataType.float32: np.float32, DataType.uint8: np.uint8, DataType.int8: np.int8}
-_OUT_OF_SCOPE = ("index construction is outside the search hot path this package replaces; "
-                 "build the index with the reference flatnav and open it with load_index()")
+_OUT_OF_SCOPE = ("not part of the path this package replaces (SURVEY.md §8): use the reference flatnav for it "
+                 "and open the saved index with load_index()")
 
 
 class _GpuIndex:
@@ -174,9 +174,37 @@ class _GpuIndex:
         d["device_ids"] = list(self._info.device_ids)[: self._info.n_devices]
         return d
 
-    # ---- construction side: out of scope ------------------------------------------------------
-    def add(self, *a, **k):
-        raise NotImplementedError(_OUT_OF_SCOPE)
+    # ---- construction --------------------------------------------------------------------------
+    def add(self, data, ef_construction: int, num_initializations: int = 100, labels=None) -> None:
+        """PyIndex::add -> addImpl (bindings.cpp:62-110, :436-443) -> Index::addBatch (Index.h:301-330).
+
+        `data`: array castable to the index dtype, shape (num_vectors, dim); `labels`: optional sequence of
+        num_vectors ints (default 0 .. num_vectors-1, as in the binding)."""
+        a = np.asarray(data)
+        if a.ndim != 2 or a.shape[1] != self._dim:
+            nd, dd = a.ndim, (a.shape[1] if a.ndim > 1 else -1)
+            raise ValueError(f"Data has incorrect dimensions. data.ndim() = `{nd}` and data_dim = `{dd}`. Expected 2D "
+                             "array with dimensions (num_vectors, dim).")
+        a = self._cast(a)
+        lab = None
+        if labels is not None:
+            try:
+                lab = np.ascontiguousarray(np.asarray(list(labels)), dtype=np.int32)
+            except (TypeError, ValueError):
+                raise ValueError("Invalid labels provided.")
+            if lab.ndim != 1 or lab.shape[0] != a.shape[0]:
+                raise ValueError("Incorrect number of labels.")
+        st = _capi.FnbBuildStats()
+        rc = _capi.lib().fnb_index_add(self._h, a.ctypes.data, lab.ctypes.data if lab is not None else None,
+                                       a.shape[0], int(ef_construction), int(num_initializations), C.byref(st))
+        self.last_build_stats = st.as_dict()
+        _capi.check(rc)
+        _capi.check(_capi.lib().fnb_index_info(self._h, C.byref(self._info)))
+
+    def reserve(self, max_node_count: int) -> None:
+        """Extension: make room for more nodes (a loaded index holds exactly its current node count)."""
+        _capi.check(_capi.lib().fnb_index_reserve(self._h, int(max_node_count)))
+        _capi.check(_capi.lib().fnb_index_info(self._h, C.byref(self._info)))
 
     def allocate_nodes(self, *a, **k):
         raise NotImplementedError(_OUT_OF_SCOPE)
@@ -233,7 +261,14 @@ def index_class(distance_type: str, index_data_type: DataType = DataType.float32
 
 def create(distance_type: str, dim: int, dataset_size: int, max_edges_per_node: int,
            index_data_type: DataType = DataType.float32, verbose: bool = False, collect_stats: bool = False):
-    """`flatnav.index.create` (bindings.cpp:484-504) builds an EMPTY index to `add()` into — construction,
-    which this package does not replace. The argument validation is kept; then it raises."""
-    index_class(distance_type, index_data_type)
-    raise NotImplementedError(_OUT_OF_SCOPE)
+    """`flatnav.index.create` (bindings.cpp:484-504): an empty index on the current CUDA device to `add()` into.
+    `verbose` prints the parameters like Index::getIndexSummary; `collect_stats` is accepted (distance counts are
+    always collected here)."""
+    cls = index_class(distance_type, index_data_type)
+    out = C.c_void_p()
+    _capi.check(_capi.lib().fnb_index_create(cls._metric, int(cls._data_type), int(dim), int(dataset_size),
+                                             int(max_edges_per_node), -1, C.byref(out)))
+    ix = cls(out.value)
+    if verbose:
+        print(f"max_edges_per_node: {max_edges_per_node}\nmax_node_count: {dataset_size}\ndimension: {dim}", flush=True)
+    return ix

@@ -98,6 +98,36 @@ int fnb_index_save(const fnb_index* index, const char* path);
 int fnb_index_info(const fnb_index* index, fnb_info* out);
 void fnb_index_free(fnb_index* index);
 
+/* ---- construction (the caller side of the search path) --------------------------------- */
+
+/* Replaces the Index constructor (include/flatnav/index/Index.h:159-180) and flatnav.index.create
+ * (python-bindings/src/flatnav/bindings.cpp:484-504): an empty index for up to max_node_count vectors on `device`
+ * (-1 = current device). */
+int fnb_index_create(int metric, int data_type, uint64_t dim, uint64_t max_node_count, uint64_t max_edges_per_node,
+                     int device, fnb_index** out);
+
+/* Grows the device arrays of a single-device index so that fnb_index_add can append up to max_node_count nodes
+ * (a loaded index holds exactly cur_num_nodes rows). */
+int fnb_index_reserve(fnb_index* index, uint64_t max_node_count);
+
+typedef struct fnb_build_stats {
+  int64_t n_added;
+  int64_t n_batches;            /* insertion batches (each: search, select + link, prune) */
+  int64_t n_dropped_backlinks;  /* back-links not considered because one node got > 96 newcomers in one batch */
+  float device_ms;              /* upload + construction, CUDA events */
+  float reserved;
+} fnb_build_stats;
+
+/* Replaces Index::addBatch / add (Index.h:301-378) with selectNeighbors (:714-763) and connectNeighbors (:765-834),
+ * and PyIndex::add (bindings.cpp:62-110): appends n vectors (HOST, row-major [n, dim] of the index data type) with
+ * their labels (HOST int32 [n]; NULL = 0 .. n-1 like the binding) and links them into the graph.  Insertion is
+ * batched on the GPU: the traversal kernel finds each new node's ef_construction nearest inserted nodes, then the
+ * reference's pruning heuristic picks max(M/2, 1) links and the back-links are merged (a full row is re-pruned to
+ * M).  The graph is not node-for-node the reference's (neither are two multi-threaded reference builds); its
+ * search quality is, and fnb_index_save writes it in the reference's format. */
+int fnb_index_add(fnb_index* index, const void* vectors, const int32_t* labels, int64_t n, int ef_construction,
+                  int num_initializations, fnb_build_stats* stats);
+
 /* ---- search ------------------------------------------------------------------------------------ */
 
 /* Replaces the batched fan-out PyIndex::searchImpl (bindings.cpp:161-228: executeInParallel over

@@ -42,8 +42,16 @@ def test_namespace_mirrors_reference():
 def test_create_validates_distance_type_like_reference():
     with pytest.raises(ValueError, match="Invalid distance type"):  # bindings.cpp:397-407
         flatnav_b200.index.create("cosine", 8, 10, 4)
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if not has_gpu:
+        with pytest.raises(RuntimeError):  # no CUDA device and no CPU path: loud failure, not a fallback
+            flatnav_b200.index.create("l2", 8, 10, 4)
     with pytest.raises(NotImplementedError):
-        flatnav_b200.index.create("l2", 8, 10, 4)
+        flatnav_b200.index.IndexL2Float.reorder(None)
     assert flatnav_b200.index.index_class("angular", DataType.uint8) is flatnav_b200.index.IndexIPUint8
     assert flatnav_b200.index.index_class("L2") is flatnav_b200.index.IndexL2Float
 
