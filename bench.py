@@ -64,6 +64,10 @@ def apply_env_overrides() -> None:
         if v:
             WORKLOAD[key] = int(v)
             WORKLOAD["name"] += f" [override {key}={v}]"
+    b = os.environ.get("FNB_BENCH_BUILDER")
+    if b:
+        WORKLOAD["builder"] = b
+        WORKLOAD["name"] += f" [override builder={b}]"
     g = os.environ.get("FNB_BENCH_GEN")
     if g:
         WORKLOAD["gen"] = g
@@ -151,7 +155,7 @@ def run_reference(args, rank: int, world: int) -> None:
     if not refbin.available():
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref reference binary cannot run on this host"}))
         return
-    path, _ = ensure_index(w["gen"], w["n"], w["dim"], w["metric"], w["M"], w["efc"])
+    path, _ = ensure_index(w["gen"], w["n"], w["dim"], w["metric"], w["M"], w["efc"], builder=w.get("builder", "reference"))
     cores = os.cpu_count() or 1
     nq = min(w["Q"], CPU_SAMPLE_Q)
     queries = make_queries(1)[0][:nq]
@@ -212,10 +216,10 @@ def main() -> None:
 
     # ---- index: built once by the reference (rank 0), then loaded by every rank onto its own GPU ----
     if rank == 0:
-        path, build_info = ensure_index(w["gen"], w["n"], w["dim"], w["metric"], w["M"], w["efc"])
+        path, build_info = ensure_index(w["gen"], w["n"], w["dim"], w["metric"], w["M"], w["efc"], builder=w.get("builder", "reference"))
     barrier()
     if rank != 0:
-        path, build_info = ensure_index(w["gen"], w["n"], w["dim"], w["metric"], w["M"], w["efc"])
+        path, build_info = ensure_index(w["gen"], w["n"], w["dim"], w["metric"], w["M"], w["efc"], builder=w.get("builder", "reference"))
     ix = flatnav_b200.index.IndexL2Float.load_index(path, devices=[local])
     info = ix.info
 

@@ -5,9 +5,9 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         tools/bench_sharded.py [--n-shard 12500000] [--q 10000] [--ef 100] [--steps 50]
 
-Each rank builds its shard with the unmodified reference (construction is out of scope; N ranks share the host's
-cores, so the default shard size is what a 16-core host builds in about a minute — state --n-shard 12500000 for
-the literal 100M / 8 configuration).  Prints one JSON line per exchange mode (rank 0): QPS (queries/s of the whole
+Each rank builds its own shard: --builder gpu (default) uses this engine's GPU construction (csrc/build.cu, a few
+seconds for 12.5M x 128 uint8, so --n-shard 12500000 gives the literal 100M / 8 configuration), --builder ref the
+unmodified reference on this rank's share of the host cores.  Prints one JSON line per exchange mode (rank 0): QPS (queries/s of the whole
 job: all ranks answer the same Q), ms per step (CUDA events, max over ranks), recall@K against the exact global
 ground truth (per-shard tensor-core brute force, merged)."""
 from __future__ import annotations
@@ -34,6 +34,7 @@ def main():
     ap.add_argument("--ef", type=int, default=100)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--builder", default="gpu", choices=["gpu", "ref"])
     args = ap.parse_args()
 
     import torch
@@ -51,19 +52,26 @@ def main():
     os.environ.setdefault("MASTER_PORT", "29533")
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
 
-    os.makedirs(CACHE, exist_ok=True)
-    path = os.path.join(CACHE, f"shard{rank}of{world}_{args.gen}_n{args.n_shard}_d{args.dim}_l2_M32_efc100.idx")
-    t0 = time.time()
-    if not os.path.exists(path):
-        data = synthetic.make(args.gen, args.n_shard, args.dim, stream=rank + 1)
-        threads = max(1, (os.cpu_count() or 1) // world)
-        refbin.build_index(data, "l2", 32, 100, path + ".tmp", threads=threads, first_label=rank * args.n_shard)
-        os.replace(path + ".tmp", path)
-        del data
-    build_s = time.time() - t0
     cls = {"latent-u8": flatnav_b200.index.IndexL2Uint8, "latent": flatnav_b200.index.IndexL2Float,
            "latent-i8": flatnav_b200.index.IndexL2Int8}[args.gen]
-    ix = cls.load_index(path, devices=[local])
+    t0 = time.time()
+    data = synthetic.make(args.gen, args.n_shard, args.dim, stream=rank + 1)
+    gen_s = time.time() - t0
+    t0 = time.time()
+    if args.builder == "gpu":
+        from flatnav_b200.data_type import DataType
+        dt = {"uint8": DataType.uint8, "float32": DataType.float32, "int8": DataType.int8}[data.dtype.name]
+        ix = flatnav_b200.index.create("l2", args.dim, args.n_shard, 32, dt)
+        ix.add(data, 100, labels=np.arange(rank * args.n_shard, (rank + 1) * args.n_shard, dtype=np.int32))
+        build_info = dict(ix.last_build_stats)
+    else:
+        os.makedirs(CACHE, exist_ok=True)
+        path = os.path.join(CACHE, f"shard{rank}of{world}_{args.gen}_n{args.n_shard}_d{args.dim}_l2_M32_efc100.idx")
+        threads = max(1, (os.cpu_count() or 1) // world)
+        build_info = refbin.build_index(data, "l2", 32, 100, path, threads=threads, first_label=rank * args.n_shard)
+        ix = cls.load_index(path, devices=[local])
+    del data
+    build_s = time.time() - t0
     q = synthetic.make(args.gen, args.q, args.dim, queries=True)
     Q, K = args.q, args.k
     dq = torch.from_numpy(q).cuda()
@@ -103,7 +111,8 @@ def main():
             print(json.dumps({"bench": "dataset-sharded search", "exchange": mode, "n_gpus": world,
                               "n_total": world * args.n_shard, "n_shard": args.n_shard, "dim": args.dim, "gen": args.gen,
                               "Q": Q, "K": K, "ef_search": args.ef, "steps": args.steps, "ms_per_step": ms,
-                              "qps": Q / (ms * 1e-3), "recall_at_k": round(rec, 4), "shard_build_s": round(build_s, 1)}),
+                              "qps": Q / (ms * 1e-3), "recall_at_k": round(rec, 4), "builder": args.builder, "shard_gen_s": round(gen_s, 1),
+                              "shard_build_s": round(build_s, 1), "shard_build": build_info}),
                   flush=True)
         sh.close()
     same = np.array_equal(results["nccl"][0], results["peer"][0]) and np.array_equal(results["nccl"][1], results["peer"][1])

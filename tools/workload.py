@@ -22,16 +22,37 @@ def index_name(gen: str, n: int, dim: int, metric: str, M: int, efc: int, rank: 
 
 
 def ensure_index(gen: str, n: int, dim: int, metric: str, M: int = 32, efc: int = 100, threads: int = 0,
-                 rank: int = 16):
-    """Return (path, info).  Builds with the reference binary if the file is not cached."""
+                 rank: int = 16, builder: str = "reference"):
+    """Return (path, info).  Builds the file if it is not cached: with the reference binary (default), or with this
+    engine's GPU construction (builder="gpu": the large configs, where the CPU build takes minutes) — either way the
+    file is in the reference's format and both arms of a benchmark read the same graph."""
     from flatnav_b200 import synthetic
     from oracle import refbin
     os.makedirs(CACHE, exist_ok=True)
-    path = os.path.join(CACHE, index_name(gen, n, dim, metric, M, efc, rank) + ".idx")
+    path = os.path.join(CACHE, index_name(gen, n, dim, metric, M, efc, rank) + ("_gpubuilt" if builder == "gpu" else "") + ".idx")
     meta = path + ".json"
     if os.path.exists(path) and os.path.exists(meta):
         info = json.load(open(meta))
         info["cached"] = True
+        return path, info
+    if builder == "gpu":
+        import numpy as np
+
+        import flatnav_b200
+        from flatnav_b200.data_type import DataType
+        t0 = time.time()
+        data = synthetic.make(gen, n, dim, rank=rank)
+        t_gen = time.time() - t0
+        dt = {"float32": DataType.float32, "uint8": DataType.uint8, "int8": DataType.int8}[data.dtype.name]
+        t0 = time.time()
+        ix = flatnav_b200.index.create("l2" if metric == "l2" else "angular", dim, n, M, dt)
+        ix.add(data, efc)
+        st = dict(ix.last_build_stats)
+        ix.save(path + ".tmp")
+        os.replace(path + ".tmp", path)
+        info = {"build_seconds": round(st["device_ms"] * 1e-3, 3), "build_and_save_seconds": round(time.time() - t0, 2),
+                "gen_seconds": round(t_gen, 2), "builder": "flatnav_b200 GPU construction", "cached": False}
+        json.dump(info, open(meta, "w"))
         return path, info
     if not refbin.available():
         raise RuntimeError("no cached index and the reference builder (oracle/_ref) cannot run on this host")
