@@ -16,6 +16,7 @@ FNB_ERR_INVALID_ARG, FNB_ERR_IO, FNB_ERR_FORMAT, FNB_ERR_CUDA, FNB_ERR_UNSUPPORT
 FNB_DTYPE_UINT8, FNB_DTYPE_INT8, FNB_DTYPE_FLOAT32, FNB_DTYPE_ANY = 0, 4, 9, -1
 FNB_METRIC_L2, FNB_METRIC_IP = 0, 1
 FNB_IPC_HANDLE_BYTES = 64
+FNB_REORDER_GORDER, FNB_REORDER_RCM = 0, 1
 
 
 class FnbInfo(C.Structure):
@@ -67,6 +68,12 @@ EXPORTS = {
     "fnb_index_reserve": (C.c_int, [C.c_void_p, C.c_uint64]),
     "fnb_index_add": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int,
                                 C.POINTER(FnbBuildStats)]),
+    "fnb_index_allocate_nodes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
+    "fnb_index_build_graph_links": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "fnb_index_links": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "fnb_index_reorder": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "fnb_graph_order": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_void_p]),
+    "fnb_index_relabel": (C.c_int, [C.c_void_p, C.c_void_p]),
     "fnb_index_save": (C.c_int, [C.c_void_p, C.c_char_p]),
     "fnb_index_info": (C.c_int, [C.c_void_p, C.POINTER(FnbInfo)]),
     "fnb_index_free": (None, [C.c_void_p]),

@@ -216,7 +216,7 @@ __global__ void __launch_bounds__(BUILD_WARPS * 32) build_prune_kernel(const Bui
 __global__ void build_init_rows_kernel(uint32_t* adj, uint32_t* deg, uint32_t first, uint32_t count, uint32_t M) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < (size_t)count * M) adj[(size_t)first * M + i] = first + (uint32_t)(i / M);
-  if (i < count) deg[first + i] = 0;
+  if (deg && i < count) deg[first + i] = 0;
 }
 // degree of loaded rows = number of links that are not self-loops (rows are packed: used slots first)
 __global__ void build_count_degree_kernel(const uint32_t* adj, uint32_t* deg, uint32_t n, uint32_t M, unsigned int* unpacked) {
@@ -304,6 +304,49 @@ using namespace fnb;
       return fail(FNB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
     }                                                                                                      \
   } while (0)
+
+// Vectors (host, dense [n][dim]) -> padded rows [cur_nodes, cur_nodes + n), labels, and optionally all-self-loop link
+// rows (Index::allocateNode, Index.h:262-272).  Does not change cur_nodes.  The caller holds ix->mu.
+int upload_new_rows_locked(fnb_index* ix, const void* vectors, const int32_t* labels, int32_t label_base, int64_t n,
+                           bool init_links) {
+  Header& h = ix->h;
+  Replica& r = ix->replicas[0];
+  int prev = 0;
+  cudaGetDevice(&prev);
+  std::vector<void*> tmp;
+  B_CU(cudaSetDevice(r.device));
+  cudaStream_t s = r.stream;
+  const uint32_t first = (uint32_t)h.cur_nodes;
+  const size_t rowb = (size_t)ix->stride * FNB_CHUNK_BYTES;
+  unsigned char* d_src = nullptr;
+  const size_t chunk_rows = std::max<size_t>(1, (size_t)(256u << 20) / h.data_size);  // 256 MB staging
+  B_CU(cudaMalloc(&d_src, std::min<size_t>(chunk_rows, (size_t)n) * h.data_size));
+  tmp.push_back(d_src);
+  for (size_t lo = 0; lo < (size_t)n; lo += chunk_rows) {
+    const size_t cnt = std::min(chunk_rows, (size_t)n - lo);
+    B_CU(cudaMemcpyAsync(d_src, (const unsigned char*)vectors + lo * h.data_size, cnt * h.data_size, cudaMemcpyHostToDevice, s));
+    build_pad_rows_kernel<<<r.num_sms * 8, 256, 0, s>>>(d_src, (uint32_t)h.data_size,
+                                                       reinterpret_cast<unsigned char*>(r.vec) + (first + lo) * rowb,
+                                                       (uint32_t)rowb, cnt);
+    B_CU(cudaGetLastError());
+    B_CU(cudaStreamSynchronize(s));  // the pageable source buffer is reused by the caller's next chunk
+  }
+  std::vector<int32_t> lab;
+  if (!labels) {
+    lab.resize(n);
+    for (int64_t i = 0; i < n; i++) lab[i] = label_base + (int32_t)i;
+    labels = lab.data();
+  }
+  B_CU(cudaMemcpy(r.labels + first, labels, (size_t)n * 4, cudaMemcpyHostToDevice));
+  if (init_links) {
+    build_init_rows_kernel<<<(unsigned)(((size_t)n * h.M + 255) / 256), 256, 0, s>>>(r.adj, nullptr, first, (uint32_t)n, (uint32_t)h.M);
+    B_CU(cudaGetLastError());
+    B_CU(cudaStreamSynchronize(s));
+  }
+  for (void* ptr : tmp) cudaFree(ptr);
+  cudaSetDevice(prev);
+  return FNB_OK;
+}
 
 extern "C" {
 
@@ -415,28 +458,15 @@ int fnb_index_add(fnb_index* ix, const void* vectors, const int32_t* labels, int
   const uint32_t max_b = (uint32_t)std::max(1, getenv("FNB_BUILD_BATCH") ? atoi(getenv("FNB_BUILD_BATCH")) : 16384);
   const uint32_t ovf_cap = max_b * Msel;
 
-  // ---- upload: vectors (padded rows), labels, self-loop rows ----
+  // ---- upload: vectors (padded rows), labels ----
   {
-    unsigned char* d_src = nullptr;
-    const size_t chunk_rows = std::max<size_t>(1, (size_t)(256u << 20) / h.data_size);  // 256 MB staging
-    B_CU(cudaMalloc(&d_src, std::min<size_t>(chunk_rows, (size_t)n) * h.data_size));
-    tmp.push_back(d_src);
-    for (size_t lo = 0; lo < (size_t)n; lo += chunk_rows) {
-      const size_t cnt = std::min(chunk_rows, (size_t)n - lo);
-      B_CU(cudaMemcpyAsync(d_src, (const unsigned char*)vectors + lo * h.data_size, cnt * h.data_size, cudaMemcpyHostToDevice, s));
-      build_pad_rows_kernel<<<r.num_sms * 8, 256, 0, s>>>(d_src, (uint32_t)h.data_size,
-                                                         reinterpret_cast<unsigned char*>(r.vec) + (first + lo) * rowb,
-                                                         (uint32_t)rowb, cnt);
-      B_CU(cudaGetLastError());
-      B_CU(cudaStreamSynchronize(s));  // the pageable source buffer is reused by the caller's next chunk
+    const int rc = upload_new_rows_locked(ix, vectors, labels, 0, n, /*init_links=*/false);  // labels NULL: 0 .. n-1 (bindings.cpp:84-86)
+    if (rc != FNB_OK) {
+      cudaEventDestroy(e0);
+      cudaEventDestroy(e1);
+      cudaSetDevice(prev);
+      return rc;
     }
-    std::vector<int32_t> lab;
-    if (!labels) {
-      lab.resize(n);
-      for (int64_t i = 0; i < n; i++) lab[i] = (int32_t)i;  // PyIndex::add without labels: 0 .. n-1 (bindings.cpp:84-86)
-      labels = lab.data();
-    }
-    B_CU(cudaMemcpy(r.labels + first, labels, (size_t)n * 4, cudaMemcpyHostToDevice));
   }
   uint32_t *deg = nullptr, *ovf_head = nullptr, *ovf_next = nullptr, *ovf_src = nullptr, *dirty = nullptr;
   unsigned int* counters = nullptr;

@@ -53,6 +53,11 @@ struct fnb_index {
   std::mutex mu;
 };
 
+// build.cu: host vectors -> padded rows [cur_nodes, cur_nodes + n), labels (NULL: label_base, label_base + 1, ...),
+// optionally all-self-loop link rows.  cur_nodes is left to the caller, who holds index->mu.
+int upload_new_rows_locked(fnb_index* ix, const void* vectors, const int32_t* labels, int32_t label_base, int64_t n,
+                           bool init_links);
+
 namespace fnb {
 int plan_search(const fnb_index* ix, int64_t Q, int K, int ef, int ninit, SearchParams* p);
 cudaError_t dispatch_search(const fnb_index* ix, const SearchParams& p, int num_sms, cudaStream_t s);

@@ -5,7 +5,8 @@ bound in python-bindings/src/flatnav/bindings.cpp:358-395, 426-474 of the refere
 argument meaning, return dtypes/shapes and exception types for `load_index`, `search`, `search_single`,
 `save`, `set_num_threads`, `num_threads`, `max_edges_per_node`, `get_query_distance_computations`, and — the caller
 side of the search path, SURVEY.md §8f — `create` / `add` (GPU batched construction, csrc/build.cu).
-`allocate_nodes`, `build_graph_links` and `reorder` stay with the reference: build or reorder there, load here.
+`allocate_nodes` / `build_graph_links` (Matrix Market link import), `get_graph_outdegree_table` and `reorder`
+(gorder / rcm, csrc/reorder.cu) complete the binding's method list.
 """
 from __future__ import annotations
 
@@ -18,8 +19,6 @@ from . import _capi
 from .data_type import DataType
 
 _NP = {DataType.float32: np.float32, DataType.uint8: np.uint8, DataType.int8: np.int8}
-_OUT_OF_SCOPE = ("not part of the path this package replaces (SURVEY.md §8): use the reference flatnav for it "
-                 "and open the saved index with load_index()")
 
 
 class _GpuIndex:
@@ -35,6 +34,7 @@ class _GpuIndex:
         # Index::loadIndex sets _num_threads = max(1, hardware_concurrency / 2)  (Index.h:467)
         self._num_threads = max(1, (os.cpu_count() or 1) // 2)
         self._n_dist = 0
+        self._label_id = 0  # PyIndex::_label_id (bindings.cpp:232): labels handed out by allocate_nodes
         self.last_stats: dict = {}
 
     def __del__(self):
@@ -206,17 +206,59 @@ class _GpuIndex:
         _capi.check(_capi.lib().fnb_index_reserve(self._h, int(max_node_count)))
         _capi.check(_capi.lib().fnb_index_info(self._h, C.byref(self._info)))
 
-    def allocate_nodes(self, *a, **k):
-        raise NotImplementedError(_OUT_OF_SCOPE)
+    def allocate_nodes(self, data):
+        """PyIndex::allocateNodes (bindings.cpp:308-324, :441-446): appends the rows of `data` as unlinked nodes
+        (every link slot a self-loop, Index.h:262-272), labelled by a running counter that starts at 0, and returns
+        the index so that `.build_graph_links(...)` can be chained.  The binding takes float32 rows and copies their
+        bytes whatever the index type; here they are cast to the index data type."""
+        a = np.asarray(data)
+        if a.ndim != 2 or a.shape[1] != self._dim:
+            raise ValueError("Data has incorrect dimensions.")
+        a = self._cast(a)
+        lab = np.arange(self._label_id, self._label_id + a.shape[0], dtype=np.int32)
+        _capi.check(_capi.lib().fnb_index_allocate_nodes(self._h, a.ctypes.data, lab.ctypes.data, a.shape[0]))
+        self._label_id += a.shape[0]
+        _capi.check(_capi.lib().fnb_index_info(self._h, C.byref(self._info)))
+        return self
 
-    def build_graph_links(self, *a, **k):
-        raise NotImplementedError(_OUT_OF_SCOPE)
+    def build_graph_links(self, mtx_filename: str) -> None:
+        """PyIndex::buildGraphLinks -> Index::buildGraphLinks (bindings.cpp:276-278, Index.h:187-238): fills the link
+        rows of allocated nodes from a Matrix Market edge list."""
+        _capi.check(_capi.lib().fnb_index_build_graph_links(self._h, os.fsencode(mtx_filename)))
 
-    def reorder(self, *a, **k):
-        raise NotImplementedError(_OUT_OF_SCOPE)
+    def get_graph_outdegree_table(self):
+        """PyIndex::getGraphOutdegreeTable -> Index::getGraphOutdegreeTable (bindings.cpp:281, Index.h:240-251):
+        for every node the list of its out-links, self-loops (unused slots) removed."""
+        n, M = int(self._info.cur_num_nodes), int(self._info.max_edges_per_node)
+        links = np.empty((n, M), dtype=np.uint32)
+        _capi.check(_capi.lib().fnb_index_links(self._h, links.ctypes.data))
+        own = np.arange(n, dtype=np.uint32)[:, None]
+        return [row[keep].tolist() for row, keep in zip(links, links != own)]
 
-    def get_graph_outdegree_table(self, *a, **k):
-        raise NotImplementedError(_OUT_OF_SCOPE)
+    def reorder(self, strategies) -> None:
+        """PyIndex::reorder -> Index::doGraphReordering (bindings.cpp:285-296, Index.h:412-427): applies `gorder`
+        (window 5) and / or `rcm` in the given sequence.  Same validation as the binding: every name is checked
+        case-insensitively first; the index then matches them case-sensitively, so `"GORDER"` passes the first check
+        and fails the second, after the strategies before it have been applied — as in the reference.
+        The last permutation (old node id -> new node id) is kept in `last_permutation`."""
+        strategies = list(strategies)
+        for st in strategies:
+            if str(st).lower() not in ("gorder", "rcm"):
+                raise ValueError("`" + str(st) + "` is not a supported graph re-ordering strategy.")
+        for st in strategies:
+            if st not in ("gorder", "rcm"):
+                raise ValueError("Invalid reordering method: " + str(st))
+            perm = np.empty(int(self._info.cur_num_nodes), dtype=np.uint32)
+            method = _capi.FNB_REORDER_GORDER if st == "gorder" else _capi.FNB_REORDER_RCM
+            _capi.check(_capi.lib().fnb_index_reorder(self._h, method, 5, perm.ctypes.data))
+            self.last_permutation = perm
+
+    def relabel(self, permutation) -> None:
+        """Index::relabel (Index.h:872-926) with a caller-supplied permutation: node i moves to row permutation[i]."""
+        perm = np.ascontiguousarray(permutation, dtype=np.uint32)
+        if perm.ndim != 1 or perm.shape[0] != int(self._info.cur_num_nodes):
+            raise ValueError("permutation must have one entry per node")
+        _capi.check(_capi.lib().fnb_index_relabel(self._h, perm.ctypes.data))
 
 
 class IndexL2Float(_GpuIndex):

@@ -128,6 +128,45 @@ typedef struct fnb_build_stats {
 int fnb_index_add(fnb_index* index, const void* vectors, const int32_t* labels, int64_t n, int ef_construction,
                   int num_initializations, fnb_build_stats* stats);
 
+/* ---- link import and graph re-ordering ------------------------------------ */
+
+/* Replaces PyIndex::allocateNodes / Index::allocateNode (bindings.cpp:308-324, Index.h:262-272): appends n vectors
+ * (HOST, row-major [n, dim] of the index data type) as unlinked nodes — every link slot a self-loop.  labels: HOST
+ * int32 [n], or NULL for cur_num_nodes, cur_num_nodes + 1, ... (the binding numbers them with a running counter). */
+int fnb_index_allocate_nodes(fnb_index* index, const void* vectors, const int32_t* labels, int64_t n);
+
+/* Replaces Index::buildGraphLinks (Index.h:187-238): reads a Matrix Market edge list (1-based "u v" lines after the
+ * '%' comments and a size line "rows cols M"); edge (u, v) takes the first slot of u's link row that still points at
+ * u, in file order; edges beyond a full row are dropped.  Same checks and messages as the reference: rows must equal
+ * max_node_count and the third number max_edges_per_node (FNB_ERR_IO, a std::runtime_error there). */
+int fnb_index_build_graph_links(fnb_index* index, const char* mtx_filename);
+
+/* Replaces Index::getGraphOutdegreeTable (Index.h:240-251) at the ABI level: copies the link table to HOST memory,
+ * uint32 [cur_num_nodes, max_edges_per_node], self-loops (unused slots) included — the caller drops them. */
+int fnb_index_links(const fnb_index* index, uint32_t* out_links);
+
+/* Replaces Index::reorderGOrder(window) / reorderRCM / one step of doGraphReordering (Index.h:412-440) with
+ * util::gOrder / util::rcmOrder (util/Reordering.h:26-199) and Index::relabel (Index.h:872-926).  The ordering is
+ * computed on the host from the link table (sequential greedy algorithms; same queue discipline as the reference, so
+ * the permutation — and the file fnb_index_save then writes — is the reference's, byte for byte); the relabelling
+ * of all links and the re-layout of vectors / link rows / labels run on the GPU on every replica.
+ * window: gorder window size, <= 0 selects the reference's default 5 (ignored for RCM).
+ * perm_out: optional HOST uint32 [cur_num_nodes], perm_out[old node id] = new node id. */
+enum { FNB_REORDER_GORDER = 0, FNB_REORDER_RCM = 1 };
+int fnb_index_reorder(fnb_index* index, int method, int window, uint32_t* perm_out);
+
+/* The ordering step of fnb_index_reorder alone, on a HOST link table uint32 [n_nodes, max_edges_per_node] (self-loops
+ * = unused slots): util::gOrder / util::rcmOrder (util/Reordering.h:26-199).  Host-only graph algorithm, needs no
+ * device; perm_out[old node id] = new node id. */
+int fnb_graph_order(const uint32_t* links, uint64_t n_nodes, uint64_t max_edges_per_node, int method, int window,
+                    uint32_t* perm_out);
+
+/* Index::relabel (Index.h:872-926) with a caller-supplied permutation (HOST uint32 [cur_num_nodes],
+ * perm[old node id] = new node id): node i moves to row perm[i], every link is mapped through perm.  Search results
+ * are unchanged up to the order of exact distance ties (labels travel with their nodes).  FNB_ERR_INVALID_ARG if
+ * perm is not a permutation. */
+int fnb_index_relabel(fnb_index* index, const uint32_t* perm);
+
 /* ---- search ------------------------------------------------------------------------------------ */
 
 /* Replaces the batched fan-out PyIndex::searchImpl (bindings.cpp:161-228: executeInParallel over

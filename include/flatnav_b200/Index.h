@@ -115,6 +115,37 @@ class Index {
                      reinterpret_cast<int32_t*>(labels), stats));
   }
 
+  // Index.h:412-440 — the ordering runs on the host (same queue discipline as util::gOrder / util::rcmOrder, so the
+  // permutation is the reference's), the relabelling and re-layout on the GPU (csrc/reorder.cu).
+  void doGraphReordering(const std::vector<std::string>& reordering_methods) {
+    for (const auto& method : reordering_methods) {
+      if (method == "gorder") {
+        reorderGOrder(5);
+      } else if (method == "rcm") {
+        reorderRCM();
+      } else {
+        throw std::invalid_argument("Invalid reordering method: " + method);
+      }
+    }
+  }
+  void reorderGOrder(const int window_size = 5) { raise(fnb_index_reorder(_h, FNB_REORDER_GORDER, window_size, nullptr)); }
+  void reorderRCM() { raise(fnb_index_reorder(_h, FNB_REORDER_RCM, 0, nullptr)); }
+
+  // Index.h:240-251
+  std::vector<std::vector<uint32_t>> getGraphOutdegreeTable() {
+    const size_t n = _info.cur_num_nodes, M = _info.max_edges_per_node;
+    std::vector<uint32_t> links(n * M);
+    raise(fnb_index_links(_h, links.data()));
+    std::vector<std::vector<uint32_t>> table(n);
+    for (size_t node = 0; node < n; node++)
+      for (size_t i = 0; i < M; i++)
+        if (links[node * M + i] != node) table[node].push_back(links[node * M + i]);
+    return table;
+  }
+
+  // Index.h:187-238
+  void buildGraphLinks(const std::string& mtx_filename) { raise(fnb_index_build_graph_links(_h, mtx_filename.c_str())); }
+
   // Index.h:492-503 — validated like the reference; GPU execution does not use it.
   inline void setNumThreads(uint32_t num_threads) {
     if (num_threads == 0 || num_threads > std::thread::hardware_concurrency()) {

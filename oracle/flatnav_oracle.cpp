@@ -31,6 +31,14 @@
 //                                  REFERENCE for this one function — pinned by a numpy float64 scan
 //                                  in tests instead), ties → lower node id.
 //
+//   ora_reorder                  — Index::doGraphReordering one step (gorder window w / rcm)
+//                                  Index.h:412-440; util::gOrder, util::rcmOrder Reordering.h:26-199;
+//                                  GorderPriorityQueue.h:13-112 (sorted vector + std::upper_bound /
+//                                  lower_bound, restated literally; the product uses an O(1) boundary
+//                                  table instead); Index::relabel Index.h:872-926 applied to the file
+//                                  image in place.  Pinned to the reference: byte-identical files.
+//   ora_build_graph_links        — Index::buildGraphLinks edge rule Index.h:219-234 (edges given as arrays).
+//
 // dist_order (float32 only; integer types are exact in any order):
 //   0 = "sequential": the scalar definition, one float accumulator, elements in index order,
 //       separate multiply and add (what defaultSquaredL2/defaultInnerProduct spell out).
@@ -403,6 +411,215 @@ int64_t ora_bruteforce(const ora_index* ixp, const void* queries, int64_t Q, int
   std::vector<std::thread> pool;
   for (int t = 0; t < threads; t++) pool.emplace_back(worker);
   for (auto& t : pool) t.join();
+  return 0;
+}
+
+}  // extern "C"
+
+// =================================================================================================
+// Graph re-ordering (Index.h:412-440, util/Reordering.h, util/GorderPriorityQueue.h) on a file image
+// =================================================================================================
+namespace {
+
+typedef std::vector<std::vector<uint32_t>> table_t;
+
+// Index::getGraphOutdegreeTable (Index.h:240-251)
+table_t outdegree_table(const ora_index& ix) {
+  table_t t(ix.cur_num_nodes);
+  for (uint32_t n = 0; n < ix.cur_num_nodes; n++) {
+    const uint32_t* links = node_links(ix, n);
+    for (uint64_t i = 0; i < ix.M; i++)
+      if (links[i] != n) t[n].push_back(links[i]);
+  }
+  return t;
+}
+
+// GorderPriorityQueue.h:13-112: entries sorted ascending by priority; the reference's hash map
+// key -> slot is a plain vector here (-1 = erased), everything else as written there.
+struct GorderPQ {
+  struct Node {
+    uint32_t key;
+    int priority;
+  };
+  std::vector<Node> list;
+  std::vector<int64_t> index;
+  static bool compare(const Node& a, const Node& b) { return a.priority < b.priority; }
+  explicit GorderPQ(size_t n) : list(n), index(n) {
+    for (size_t i = 0; i < n; i++) {
+      list[i] = Node{(uint32_t)i, 0};
+      index[i] = (int64_t)i;
+    }
+  }
+  void swap(size_t i, size_t j) {
+    Node tmp = list[i];
+    list[i] = list[j];
+    list[j] = tmp;
+    index[list[i].key] = (int64_t)i;
+    index[list[j].key] = (int64_t)j;
+  }
+  void increment(uint32_t key) {
+    if (index[key] < 0) return;
+    const size_t i = (size_t)index[key];
+    auto it = std::upper_bound(list.begin(), list.end(), list[i], compare);
+    const size_t new_index = (size_t)(it - list.begin()) - 1;
+    swap(i, new_index);
+    list[new_index].priority++;
+  }
+  void decrement(uint32_t key) {
+    if (index[key] < 0) return;
+    const size_t i = (size_t)index[key];
+    auto it = std::lower_bound(list.begin(), list.end(), list[i], compare);
+    const size_t new_index = (size_t)(it - list.begin());
+    swap(i, new_index);
+    list[new_index].priority--;
+  }
+  uint32_t pop() {
+    Node max = list.back();
+    list.pop_back();
+    index[max.key] = -1;
+    return max.key;
+  }
+};
+
+// util::gOrder (Reordering.h:26-117)
+std::vector<uint32_t> gorder(const table_t& out, int w) {
+  const int64_t n = (int64_t)out.size();
+  table_t in(n);
+  for (int64_t node = 0; node < n; node++)
+    for (uint32_t edge : out[node]) in[edge].push_back((uint32_t)node);
+  GorderPQ Q(n);
+  std::vector<uint32_t> P(n, 0);
+  if (n == 0) return P;
+  Q.increment(0);
+  P[0] = Q.pop();
+  for (int64_t i = 1; i < n; i++) {
+    const uint32_t v_e = P[i - 1];
+    for (uint32_t u : out[v_e]) Q.increment(u);
+    for (uint32_t u : in[v_e]) {
+      Q.increment(u);
+      for (uint32_t v : out[u]) Q.increment(v);
+    }
+    if (i > w + 1) {
+      const uint32_t v_b = P[i - w - 1];
+      for (uint32_t u : out[v_b]) Q.decrement(u);
+      for (uint32_t u : in[v_b]) {
+        Q.decrement(u);
+        for (uint32_t v : out[u]) Q.decrement(v);
+      }
+    }
+    P[i] = Q.pop();
+  }
+  std::vector<uint32_t> Pinv(n, 0);
+  for (int64_t k = 0; k < n; k++) Pinv[P[k]] = (uint32_t)k;
+  return Pinv;
+}
+
+// util::rcmOrder (Reordering.h:119-199)
+std::vector<uint32_t> rcm(const table_t& out) {
+  const size_t n = out.size();
+  typedef std::pair<uint32_t, int> nd_t;
+  auto less_degree = [](const nd_t& a, const nd_t& b) { return a.second < b.second; };
+  std::vector<nd_t> sorted_nodes;
+  std::vector<int> degrees;
+  for (size_t node = 0; node < n; node++) {
+    const int deg = (int)out[node].size();
+    sorted_nodes.push_back({(uint32_t)node, deg});
+    degrees.push_back(deg);
+  }
+  std::sort(sorted_nodes.begin(), sorted_nodes.end(), less_degree);
+  std::vector<uint32_t> P;
+  std::vector<bool> visited(n, false);
+  for (size_t i = 0; i < sorted_nodes.size(); i++) {
+    const uint32_t node = sorted_nodes[i].first;
+    std::queue<uint32_t> Q;
+    if (visited[node]) continue;
+    P.push_back(node);
+    visited[node] = true;
+    std::vector<nd_t> neighbors;
+    for (uint32_t edge : out[node]) neighbors.push_back({edge, degrees[edge]});
+    std::sort(neighbors.begin(), neighbors.end(), less_degree);
+    for (auto& x : neighbors) Q.push(x.first);
+    while (!Q.empty()) {
+      const uint32_t candidate = Q.front();
+      Q.pop();
+      if (visited[candidate]) continue;
+      P.push_back(candidate);
+      visited[candidate] = true;
+      std::vector<nd_t> cn;
+      for (uint32_t edge : out[candidate]) cn.push_back({edge, degrees[edge]});
+      std::sort(cn.begin(), cn.end(), less_degree);
+      for (auto& x : cn) Q.push(x.first);
+    }
+  }
+  std::reverse(P.begin(), P.end());
+  std::vector<uint32_t> Pinv(n, 0);
+  for (size_t k = 0; k < n; k++) Pinv[P[k]] = (uint32_t)k;
+  return Pinv;
+}
+
+// Index::relabel (Index.h:872-926) + swapNodes (:575-592) on the node blob, in place
+void relabel(const ora_index& ix, uint8_t* mem, const std::vector<uint32_t>& P) {
+  const uint64_t ns = ix.node_size_bytes;
+  for (uint32_t n = 0; n < ix.cur_num_nodes; n++) {
+    uint32_t* links = reinterpret_cast<uint32_t*>(mem + (uint64_t)n * ns + ix.data_size_bytes);
+    for (uint64_t m = 0; m < ix.M; m++) links[m] = P[links[m]];
+  }
+  std::vector<uint8_t> temp(ns);
+  auto swap_nodes = [&](uint32_t a, uint32_t b) {  // whole node = data + links + label
+    std::memcpy(temp.data(), mem + (uint64_t)b * ns, ns);
+    std::memmove(mem + (uint64_t)b * ns, mem + (uint64_t)a * ns, ns);
+    std::memcpy(mem + (uint64_t)a * ns, temp.data(), ns);
+  };
+  std::vector<bool> relocated(ix.cur_num_nodes, false);
+  for (uint32_t n = 0; n < ix.cur_num_nodes; n++) {
+    if (relocated[n]) continue;
+    const uint32_t src = n;
+    uint32_t dest = P[src];
+    swap_nodes(src, dest);
+    relocated[src] = true;
+    while (!relocated[dest]) {
+      relocated[dest] = true;
+      dest = P[dest];
+      swap_nodes(src, dest);
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+// One step of Index::doGraphReordering on a WRITABLE file image.  method 0 = gorder (window w), 1 = rcm.
+// perm_out (nullable): uint32 [cur_num_nodes], old id -> new id.
+int ora_reorder(void* file_bytes, uint64_t nbytes, int method, int w, uint32_t* perm_out) {
+  ora_index ix;
+  int rc = ora_parse_header(file_bytes, nbytes, ORA_L2, &ix);
+  if (rc != 0) return rc;
+  if (method != 0 && method != 1) return -20;
+  table_t out = outdegree_table(ix);
+  std::vector<uint32_t> P = method == 0 ? gorder(out, w) : rcm(out);
+  relabel(ix, static_cast<uint8_t*>(file_bytes) + 60, P);
+  if (perm_out)
+    for (size_t i = 0; i < P.size(); i++) perm_out[i] = P[i];
+  return 0;
+}
+
+// Edge rule of Index::buildGraphLinks (Index.h:219-234) on a WRITABLE file image; edges 0-based, file order.
+int ora_build_graph_links(void* file_bytes, uint64_t nbytes, const uint32_t* src, const uint32_t* dst, uint64_t n_edges) {
+  ora_index ix;
+  int rc = ora_parse_header(file_bytes, nbytes, ORA_L2, &ix);
+  if (rc != 0) return rc;
+  uint8_t* mem = static_cast<uint8_t*>(file_bytes) + 60;
+  for (uint64_t e = 0; e < n_edges; e++) {
+    const uint32_t u = src[e], v = dst[e];
+    uint32_t* links = reinterpret_cast<uint32_t*>(mem + (uint64_t)u * ix.node_size_bytes + ix.data_size_bytes);
+    for (uint64_t i = 0; i < ix.M; i++) {
+      if (links[i] == u) {
+        links[i] = v;
+        break;
+      }
+    }
+  }
   return 0;
 }
 

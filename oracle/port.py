@@ -57,7 +57,40 @@ def lib() -> C.CDLL:
         _lib.ora_bruteforce.restype = C.c_int64
         _lib.ora_bruteforce.argtypes = [C.POINTER(_OraIndex), C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int,
                                         C.c_void_p, C.c_void_p]
+        _lib.ora_reorder.restype = C.c_int
+        _lib.ora_reorder.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_void_p]
+        _lib.ora_build_graph_links.restype = C.c_int
+        _lib.ora_build_graph_links.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64]
     return _lib
+
+
+GORDER, RCM = 0, 1
+
+
+def reorder_file(blob, strategies, window: int = 5):
+    """Index::doGraphReordering (Index.h:412-427) on the bytes of an index file.  Returns (new file bytes as a
+    uint8 array, list of permutations old id -> new id, one per strategy)."""
+    buf = np.array(np.frombuffer(blob, dtype=np.uint8))  # writable copy
+    n = int(np.frombuffer(buf[4 + 32:4 + 40].tobytes(), dtype=np.uint64)[0])  # cur_num_nodes
+    perms = []
+    for st in strategies:
+        perm = np.empty(n, dtype=np.uint32)
+        rc = lib().ora_reorder(buf.ctypes.data, buf.size, {"gorder": GORDER, "rcm": RCM}[st], window, perm.ctypes.data)
+        if rc != 0:
+            raise ValueError(f"ora_reorder failed with {rc}")
+        perms.append(perm)
+    return buf, perms
+
+
+def build_graph_links_file(blob, src, dst):
+    """Edge rule of Index::buildGraphLinks (Index.h:219-234) on the bytes of an index file; 0-based edges."""
+    buf = np.array(np.frombuffer(blob, dtype=np.uint8))
+    src = np.ascontiguousarray(src, dtype=np.uint32)
+    dst = np.ascontiguousarray(dst, dtype=np.uint32)
+    rc = lib().ora_build_graph_links(buf.ctypes.data, buf.size, src.ctypes.data, dst.ctypes.data, src.size)
+    if rc != 0:
+        raise ValueError(f"ora_build_graph_links failed with {rc}")
+    return buf
 
 
 class OracleIndex:

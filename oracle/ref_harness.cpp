@@ -19,6 +19,11 @@
 //   ref_flatnav search <l2|ip> <f32|u8|i8> <index.idx> <queries.bin> <Q> <K> <ef> <ninit>
 //                      <threads> <reps> <out_prefix|->
 //   ref_flatnav info   <l2|ip> <f32|u8|i8> <index.idx>
+//   ref_flatnav reorder <l2|ip> <f32|u8|i8> <in.idx> <out.idx> <gorder|rcm>[,<gorder|rcm>...]
+//                      Index::loadIndex + doGraphReordering (Index.h:412-427) + saveIndex
+//   ref_flatnav mtx    <l2|ip> <f32|u8|i8> <data.bin> <N> <D> <M> <graph.mtx> <out.idx>
+//                      Index::allocateNode per row (labels 0..N-1, bindings.cpp:308-324) + buildGraphLinks
+//                      (Index.h:187-238) + saveIndex
 
 #include <algorithm>
 #include <atomic>
@@ -146,6 +151,38 @@ static int do_search(char** a, int nargs) {
 }
 
 template <typename dist_t>
+static int do_reorder(char** a) {
+  auto index = Index<dist_t, int>::loadIndex(a[0]);
+  std::vector<std::string> methods;
+  std::stringstream ss(a[2]);
+  for (std::string m; std::getline(ss, m, ',');) methods.push_back(m);
+  auto t0 = std::chrono::steady_clock::now();
+  index->doGraphReordering(methods);
+  double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  index->saveIndex(a[1]);
+  std::printf("{\"op\":\"reorder\",\"methods\":\"%s\",\"seconds\":%.3f}\n", a[2], secs);
+  return 0;
+}
+
+template <typename dist_t, typename elem_t>
+static int do_mtx(DataType dt, char** a) {
+  size_t N = std::strtoull(a[1], nullptr, 10), D = std::strtoull(a[2], nullptr, 10);
+  int M = std::atoi(a[3]);
+  auto data = read_file(a[0], N * D * sizeof(elem_t));
+  auto dist = std::make_unique<dist_t>(D);
+  auto index = std::make_unique<Index<dist_t, int>>(std::move(dist), (int)N, M, /*collect_stats=*/false, dt);
+  for (size_t i = 0; i < N; i++) {
+    int label = (int)i;
+    uint32_t id;
+    index->allocateNode((void*)(data.data() + i * D * sizeof(elem_t)), label, id);
+  }
+  index->buildGraphLinks(a[4]);
+  index->saveIndex(a[5]);
+  std::printf("{\"op\":\"mtx\",\"N\":%zu}\n", N);
+  return 0;
+}
+
+template <typename dist_t>
 static int do_info(char** a) {
   auto index = Index<dist_t, int>::loadIndex(a[0]);
   std::printf(
@@ -161,6 +198,8 @@ static int run(const std::string& op, DataType dt, char** a, int n) {
   if (op == "build" && n >= 7) return do_build<dist_t, elem_t>(dt, a, n);
   if (op == "search" && n >= 9) return do_search<dist_t, elem_t>(a, n);
   if (op == "info" && n >= 1) return do_info<dist_t>(a);
+  if (op == "reorder" && n >= 3) return do_reorder<dist_t>(a);
+  if (op == "mtx" && n >= 6) return do_mtx<dist_t, elem_t>(dt, a);
   std::fprintf(stderr, "bad arguments for %s\n", op.c_str());
   return 2;
 }

@@ -88,3 +88,18 @@ def search(index_path: str, metric: str, queries: np.ndarray, K: int, ef: int, n
         d = np.fromfile(prefix + ".dist.bin", dtype=np.float32).reshape(Q, K)
         l = np.fromfile(prefix + ".label.bin", dtype=np.int32).reshape(Q, K)
     return d, l, info
+
+
+def reorder(index_path: str, metric: str, dtype: str, strategies, out_path: str, timeout: float | None = None) -> dict:
+    """Index::loadIndex + doGraphReordering(strategies) + saveIndex with the reference itself (Index.h:412-427).
+    `dtype` is "f32", "u8" or "i8"."""
+    return _run(["reorder", metric, dtype, index_path, out_path, ",".join(strategies)], timeout=timeout)
+
+
+def import_mtx(data: np.ndarray, metric: str, M: int, mtx_path: str, out_path: str, timeout: float | None = None) -> dict:
+    """allocateNode for every row + buildGraphLinks(mtx) + saveIndex with the reference itself (Index.h:187-272)."""
+    data = np.ascontiguousarray(data)
+    with tempfile.NamedTemporaryFile(suffix=".bin", dir=os.path.dirname(os.path.abspath(out_path))) as f:
+        data.tofile(f.name)
+        return _run(["mtx", metric, DT[data.dtype], f.name, str(data.shape[0]), str(data.shape[1]), str(M), mtx_path,
+                     out_path], timeout=timeout)

@@ -77,6 +77,22 @@ int main(int argc, char** argv) {
     return 19;
   } catch (const std::runtime_error&) { checks++; }
 
+  // re-ordering (Index.h:412-440): the saved file is compared with the reference's by the caller
+  {
+    auto r = Index<SquaredL2Distance<DataType::float32>, int>::loadIndex(idx);
+    auto table = r->getGraphOutdegreeTable();  // Index.h:240-251
+    if (table.size() != r->currentNumNodes()) return 21;
+    for (size_t n = 0; n < table.size(); n++)
+      for (auto v : table[n])
+        if (v == n || v >= table.size()) return 22;
+    try {
+      r->doGraphReordering({"rcm", "nope"});
+      return 23;
+    } catch (const std::invalid_argument&) { checks++; }  // Index.h:421-423, after "rcm" has been applied
+    r->reorderGOrder();
+    r->saveIndex(out + ".rcm_gorder.idx");
+  }
+
   auto moved = std::move(*index);  // move-only ownership (Index.h:86-132)
   if (moved.currentNumNodes() == 0) return 20;
 

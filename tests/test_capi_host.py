@@ -50,8 +50,8 @@ def test_create_validates_distance_type_like_reference():
     if not has_gpu:
         with pytest.raises(RuntimeError):  # no CUDA device and no CPU path: loud failure, not a fallback
             flatnav_b200.index.create("l2", 8, 10, 4)
-    with pytest.raises(NotImplementedError):
-        flatnav_b200.index.IndexL2Float.reorder(None)
+    for name in ("reorder", "allocate_nodes", "build_graph_links", "get_graph_outdegree_table"):
+        assert callable(getattr(flatnav_b200.index.IndexL2Float, name))  # the binding's method list, bindings.cpp:436-473
     assert flatnav_b200.index.index_class("angular", DataType.uint8) is flatnav_b200.index.IndexIPUint8
     assert flatnav_b200.index.index_class("L2") is flatnav_b200.index.IndexL2Float
 

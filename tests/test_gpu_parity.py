@@ -292,7 +292,11 @@ def test_cpp_shim_end_to_end(tmp_path):
     r = subprocess.run([exe, golden_index_path(case["name"]), qp, str(g["queries"].shape[0]), str(K), str(ef), out],
                        capture_output=True, text=True)
     assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
-    assert "shim ok, 4 exception checks" in r.stdout
+    assert "shim ok, 5 exception checks" in r.stdout
+    import hashlib
+    import json
+    want = json.load(open(os.path.join(ROOT, "tests", "golden", "reorder.json")))["reorder"][case["name"]]["rcm,gorder"]
+    assert hashlib.sha256(open(out + ".rcm_gorder.idx", "rb").read()).hexdigest() == want["sha256"]
     d = np.fromfile(out + ".dist.bin", dtype=np.float32).reshape(-1, K)
     l = np.fromfile(out + ".label.bin", dtype=np.int32).reshape(-1, K)
     do, lo = port.OracleIndex(golden_index_path(case["name"]), port.L2).search(g["queries"], K, ef, mode=port.MODE_LIST)
