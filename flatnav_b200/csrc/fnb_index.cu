@@ -306,8 +306,10 @@ static int ensure_workspace(Replica* r, size_t dev_bytes, size_t host_bytes) {
     if (r->h_pinned) CU(cudaFreeHost(r->h_pinned));
     r->h_pinned = nullptr;
     r->h_pinned_bytes = 0;
+    if (host_bytes < 65536) host_bytes = 65536;
     CU(cudaMallocHost(&r->h_pinned, host_bytes));
     r->h_pinned_bytes = host_bytes;
+    CU(cudaHostGetDevicePointer((void**)&r->h_pinned_dev, r->h_pinned, 0));
   }
   return FNB_OK;
 }
@@ -443,7 +445,8 @@ int fnb_search_device(fnb_index* ix, int replica, const void* d_queries, int64_t
   p.out_nhops = d_nhops;
   p.counter = r.counter;
   p.totals = r.totals;
-  CU(cudaMemsetAsync(r.counter, 0, 4, s));
+  p.lat = choose_latency_variant(Q, r.num_sms);
+  if (!p.lat) CU(cudaMemsetAsync(r.counter, 0, 4, s));
   CU(cudaMemsetAsync(r.totals, 0, 24, s));
   cudaError_t e = dispatch_search(ix, p, r.num_sms, s);
   cudaSetDevice(prev);
@@ -501,6 +504,8 @@ int fnb_search(fnb_index* ix, const void* queries, int64_t Q, int K, int ef_sear
   struct Part {
     int64_t q0, nq;
     unsigned char *d_q, *d_dist, *d_label;
+    bool staged;  // small batch: everything goes through the replica's pinned staging block, no copies on the stream
+    size_t off_dist, off_label, off_nd, off_nh, off_len;
   };
   std::vector<Part> parts(R);
   // enqueue everything on every replica first, then wait: replicas run concurrently from one host thread
@@ -509,9 +514,51 @@ int fnb_search(fnb_index* ix, const void* queries, int64_t Q, int K, int ef_sear
     Part& pt = parts[i];
     pt.q0 = std::min<int64_t>(Q, per * i);
     pt.nq = std::min<int64_t>(Q, per * (i + 1)) - pt.q0;
+    pt.staged = false;
     if (pt.nq <= 0) continue;
     CU(cudaSetDevice(r.device));
-    const size_t qb = (size_t)pt.nq * h.data_size, ob = (size_t)pt.nq * K * 4;
+    const size_t qb = (size_t)pt.nq * h.data_size, ob = (size_t)pt.nq * K * 4, cb = (size_t)pt.nq * 4;
+    SearchParams p = p0;
+    p.Q = (uint32_t)pt.nq;
+    p.vec = r.vec;
+    p.adj = r.adj;
+    p.labels = r.labels;
+    p.lat = choose_latency_variant(pt.nq, r.num_sms);
+    // Small batches (search_single above all) are bounded by host and launch overhead, not by the kernel: the
+    // queries are copied by the CPU into a pinned block the kernel reads in place, results and per-query counters
+    // are written by the kernel straight into that block (plain stores, no device totals to clear or fetch), and
+    // the only things on the stream are the kernel and the two events that time it.
+    pt.staged = p.lat && !getenv("FNB_NO_STAGING") && qb + 2 * ob + 3 * cb <= (size_t)(1u << 20);
+    if (pt.staged) {
+      pt.off_dist = align256(qb);
+      pt.off_label = pt.off_dist + align256(ob);
+      pt.off_nd = pt.off_label + align256(ob);
+      pt.off_nh = pt.off_nd + align256(cb);
+      pt.off_len = pt.off_nh + align256(cb);
+      rc = ensure_workspace(&r, 0, pt.off_len + align256(cb));
+      if (rc != FNB_OK) {
+        cudaSetDevice(prev);
+        return rc;
+      }
+      memcpy(r.h_pinned, (const unsigned char*)queries + (size_t)pt.q0 * h.data_size, qb);
+      unsigned char* dp = r.h_pinned_dev;
+      p.queries = dp;
+      p.out_dist = reinterpret_cast<float*>(dp + pt.off_dist);
+      p.out_label = reinterpret_cast<int32_t*>(dp + pt.off_label);
+      p.out_ndist = reinterpret_cast<uint32_t*>(dp + pt.off_nd);
+      p.out_nhops = reinterpret_cast<uint32_t*>(dp + pt.off_nh);
+      p.out_len = reinterpret_cast<uint32_t*>(dp + pt.off_len);
+      p.counter = nullptr;
+      p.totals = nullptr;
+      CU(cudaEventRecord(r.ev[1], r.stream));
+      cudaError_t e = dispatch_search(ix, p, r.num_sms, r.stream);
+      if (e != cudaSuccess) {
+        cudaSetDevice(prev);
+        return fail(FNB_ERR_CUDA, "search kernel launch failed: %s", cudaGetErrorString(e));
+      }
+      CU(cudaEventRecord(r.ev[2], r.stream));
+      continue;
+    }
     rc = ensure_workspace(&r, (zq ? 0 : align256(qb)) + (zd ? 0 : 2 * align256(ob)) + 256, 0);
     if (rc != FNB_OK) {
       cudaSetDevice(prev);
@@ -520,11 +567,6 @@ int fnb_search(fnb_index* ix, const void* queries, int64_t Q, int K, int ef_sear
     pt.d_q = zq ? zq + (size_t)pt.q0 * h.data_size : r.ws;
     pt.d_dist = zd ? zd + (size_t)pt.q0 * K * 4 : r.ws + (zq ? 0 : align256(qb));
     pt.d_label = zd ? zl + (size_t)pt.q0 * K * 4 : pt.d_dist + align256(ob);
-    SearchParams p = p0;
-    p.Q = (uint32_t)pt.nq;
-    p.vec = r.vec;
-    p.adj = r.adj;
-    p.labels = r.labels;
     p.queries = pt.d_q;
     if (((uintptr_t)pt.d_q & 15u) != 0) p.query_vec_ok = 0;
     p.out_dist = reinterpret_cast<float*>(pt.d_dist);
@@ -535,7 +577,7 @@ int fnb_search(fnb_index* ix, const void* queries, int64_t Q, int K, int ef_sear
     if (!zq)
       CU(cudaMemcpyAsync(pt.d_q, (const unsigned char*)queries + (size_t)pt.q0 * h.data_size, qb,
                          cudaMemcpyHostToDevice, r.stream));
-    CU(cudaMemsetAsync(r.counter, 0, 4, r.stream));
+    if (!p.lat) CU(cudaMemsetAsync(r.counter, 0, 4, r.stream));
     CU(cudaMemsetAsync(r.totals, 0, 24, r.stream));
     CU(cudaEventRecord(r.ev[1], r.stream));
     cudaError_t e = dispatch_search(ix, p, r.num_sms, r.stream);
@@ -555,17 +597,33 @@ int fnb_search(fnb_index* ix, const void* queries, int64_t Q, int K, int ef_sear
   float kms = 0.f, tms = 0.f;
   int launches = 0;
   for (int i = 0; i < R; i++) {
-    if (parts[i].nq <= 0) continue;
+    const Part& pt = parts[i];
+    if (pt.nq <= 0) continue;
     Replica& r = ix->replicas[i];
     CU(cudaSetDevice(r.device));
     CU(cudaStreamSynchronize(r.stream));
-    const unsigned long long* t = r.h_totals;
-    nd += (int64_t)t[0];
-    nh += (int64_t)t[1];
-    ns += (int64_t)t[2];
     float a = 0.f, b = 0.f;
     CU(cudaEventElapsedTime(&a, r.ev[1], r.ev[2]));
-    CU(cudaEventElapsedTime(&b, r.ev[0], r.ev[3]));
+    if (pt.staged) {
+      const size_t ob = (size_t)pt.nq * K * 4;
+      memcpy(out_dist + (size_t)pt.q0 * K, r.h_pinned + pt.off_dist, ob);
+      memcpy(out_label + (size_t)pt.q0 * K, r.h_pinned + pt.off_label, ob);
+      const uint32_t* c_nd = reinterpret_cast<const uint32_t*>(r.h_pinned + pt.off_nd);
+      const uint32_t* c_nh = reinterpret_cast<const uint32_t*>(r.h_pinned + pt.off_nh);
+      const uint32_t* c_len = reinterpret_cast<const uint32_t*>(r.h_pinned + pt.off_len);
+      for (int64_t q = 0; q < pt.nq; q++) {
+        nd += c_nd[q];
+        nh += c_nh[q];
+        ns += c_len[q] < (uint32_t)K ? 1 : 0;
+      }
+      b = a;
+    } else {
+      const unsigned long long* t = r.h_totals;
+      nd += (int64_t)t[0];
+      nh += (int64_t)t[1];
+      ns += (int64_t)t[2];
+      CU(cudaEventElapsedTime(&b, r.ev[0], r.ev[3]));
+    }
     kms = std::max(kms, a);
     tms = std::max(tms, b);
     launches++;

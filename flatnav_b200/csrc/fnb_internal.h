@@ -34,7 +34,8 @@ struct Replica {
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   unsigned char* ws = nullptr;  // device workspace of the host-buffer entry points
   size_t ws_bytes = 0;
-  unsigned char* h_pinned = nullptr;
+  unsigned char* h_pinned = nullptr;      // pinned staging block of the small-batch path
+  unsigned char* h_pinned_dev = nullptr;  // its device-side alias
   size_t h_pinned_bytes = 0;
   uint64_t device_bytes = 0;
   uint64_t capacity = 0;  // rows the vec / adj / labels arrays can hold (>= cur_nodes; construction grows it)

@@ -30,6 +30,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "fnb_layout.h"
 
@@ -54,6 +55,12 @@ __host__ __device__ constexpr int fnb_min_ctas(int ch) {
   return ch <= 1 ? FNB_CTAS_TINY_ROWS : (ch <= 4 ? FNB_CTAS_SHORT_ROWS : (ch <= 8 ? 4 : 3));
 }
 __host__ __device__ constexpr int fnb_batches_in_flight(int ch) { return ch >= 4 ? 1 : 4 / ch; }
+// Latency variant (few queries, one warp per CTA, registers are free): hold as many warp-wide load batches in
+// registers as ~96 staging registers allow, up to all 32 rows of an expansion, so that one hop costs ONE HBM round
+// trip for its rows instead of one per batch.
+__host__ __device__ constexpr int fnb_batches_in_flight_lat(int g, int ch) {
+  return (24 / ch < 1) ? 1 : ((24 / ch > g) ? g : 24 / ch);  // g = 32 / rows-per-instruction = batches per 32 rows
+}
 #define FNB_FULL 0xffffffffu
 #define FNB_EMPTY 0xffffffffu
 
@@ -66,6 +73,7 @@ struct SearchParams {
   int32_t* __restrict__ out_label;     // [Q][K]
   uint32_t* __restrict__ out_ndist;    // [Q] or null
   uint32_t* __restrict__ out_nhops;    // [Q] or null
+  uint32_t* __restrict__ out_len;      // [Q] or null: results found per query (< K = short result)
   unsigned int* counter;               // persistent-warp work counter (zeroed before launch)
   unsigned long long* totals;          // [3]: sum n_dist, sum n_hops, #short results
   uint32_t N, M, dim, nchunks, stride;
@@ -80,6 +88,7 @@ struct SearchParams {
   uint32_t query_vec_ok;  // 1 => query rows are 16-byte aligned and a whole number of chunks
   uint32_t query_pitch_chunks;  // != 0 => queries are rows of a padded vector array with this pitch (construction:
                                 // the new nodes' own rows); chunks beyond the data are zero there
+  uint32_t lat;  // 1 => latency variant (few queries): one warp per CTA, query = blockIdx.x (grid-stride), `counter` unused
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -234,12 +243,12 @@ __device__ __forceinline__ uint4 load_query_chunk(const SearchParams& p, uint32_
 // EXACT: the row is exactly G*CH chunks (e.g. D=128 f32 with G=8, CH=4): no per-chunk bounds test.
 // prefetch: rows beyond the first register batch are pulled into L2 right away (prefetch.global.L2 costs no
 // registers), so the later register batches pay an L2 hit instead of another HBM round trip each.
-template <int DT, int METRIC, int G, int CH, bool EXACT>
+template <int DT, int METRIC, int G, int CH, bool EXACT, int UU = 0>
 __device__ __forceinline__ float batch_distance(const SearchParams& p, const uint4 (&q)[CH], uint32_t my_id,
                                                 bool valid, uint32_t* s_ids, int lane, bool prefetch) {
   typedef Arith<DT, METRIC> A;
   constexpr int RPI = 32 / G;                                   // rows per warp-wide load instruction
-  constexpr int U = fnb_batches_in_flight(CH);  // warp-wide load batches held in registers
+  constexpr int U = UU > 0 ? UU : fnb_batches_in_flight(CH);  // warp-wide load batches held in registers
   const unsigned mask = __ballot_sync(FNB_FULL, valid);
   const int n = __popc(mask);
   const int myrank = __popc(mask & ((1u << lane) - 1u));
@@ -358,6 +367,28 @@ __device__ __forceinline__ bool visited_test_and_set(uint32_t* tab, const Search
   }
 }
 
+// Read-only membership test (speculative prefetch of the latency variant): true iff `id` is in the set.
+__device__ __forceinline__ bool visited_peek(uint32_t* tab, const SearchParams& p, uint32_t id) {
+  const uint32_t h = (id * 0x9E3779B1u) << p.vs_shift;
+  const uint32_t bucket = __umulhi(h, p.vs_buckets);
+  const uint32_t tag = (h >> p.vs_shift) & p.vs_tag_mask;
+  uint4* bp = reinterpret_cast<uint4*>(tab) + bucket;
+  uint4 w;
+  asm volatile("ld.volatile.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w)
+               : "r"((uint32_t)__cvta_generic_to_shared(bp)));
+  if (!p.vs_wide) {
+    const uint32_t t2 = tag | (tag << 16);
+    uint32_t x, hit = 0;
+    x = w.x ^ t2; hit |= (x - 0x00010001u) & ~x;
+    x = w.y ^ t2; hit |= (x - 0x00010001u) & ~x;
+    x = w.z ^ t2; hit |= (x - 0x00010001u) & ~x;
+    x = w.w ^ t2; hit |= (x - 0x00010001u) & ~x;
+    return (hit & 0x80008000u) != 0u;
+  }
+  return w.x == tag || w.y == tag || w.z == tag || w.w == tag;
+}
+
 __device__ __forceinline__ void visited_clear(uint32_t* tab, uint32_t buckets, int lane) {
   uint4* t4 = reinterpret_cast<uint4*>(tab);
   const uint4 e = make_uint4(FNB_EMPTY, FNB_EMPTY, FNB_EMPTY, FNB_EMPTY);
@@ -426,8 +457,19 @@ __device__ __forceinline__ void merge_accepted(volatile uint64_t* list, uint32_t
 }
 
 // ---------------------------------------------------------------------------------------------------
-template <int DT, int METRIC, int G, int CH, bool EXACT>
-__global__ void __launch_bounds__(FNB_WARPS_PER_CTA * 32, fnb_min_ctas(CH)) fnb_search_kernel(const SearchParams p) {
+// LAT = latency variant, chosen by the host when the batch is too small to fill the machine (search_single, small
+// batches): the same algorithm and arithmetic, bit for bit, but tuned for the length of ONE query's dependency chain
+// instead of for resident warps —
+//   * one warp per CTA, no register cap: every row of an expansion is loaded in one go (fnb_batches_in_flight_lat),
+//     so a hop pays one HBM round trip for its rows rather than one per register batch;
+//   * the adjacency row of every fresh neighbour is prefetched into L2 together with its vector, so whichever of
+//     them is expanded later finds its links in L2;
+//   * speculation that cannot change the result: while the current node's rows are in flight, the links of the
+//     runner-up candidate (the most likely next expansion) are read, filtered through the visited set READ-ONLY, and
+//     their vector rows prefetched into L2.
+template <int DT, int METRIC, int G, int CH, bool EXACT, bool LAT>
+__global__ void __launch_bounds__(LAT ? 32 : FNB_WARPS_PER_CTA * 32, LAT ? 1 : fnb_min_ctas(CH))
+    fnb_search_kernel(const SearchParams p) {
   extern __shared__ __align__(16) unsigned char fnb_smem[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -436,11 +478,18 @@ __global__ void __launch_bounds__(FNB_WARPS_PER_CTA * 32, fnb_min_ctas(CH)) fnb_
   uint32_t* tab = reinterpret_cast<uint32_t*>(wbase + (size_t)p.Bcap * 8);
   uint32_t* s_ids = tab + p.vs_buckets * 4;
   const int pos = lane % G;
+  constexpr int UL = LAT ? fnb_batches_in_flight_lat(G, CH) : 0;  // 0: the throughput variant's default
+  uint32_t qi_next = blockIdx.x;
 
   for (;;) {
     uint32_t qi = 0;
-    if (lane == 0) qi = atomicAdd(p.counter, 1u);
-    qi = __shfl_sync(FNB_FULL, qi, 0);
+    if (LAT) {
+      qi = qi_next;
+      qi_next += gridDim.x;
+    } else {
+      if (lane == 0) qi = atomicAdd(p.counter, 1u);
+      qi = __shfl_sync(FNB_FULL, qi, 0);
+    }
     if (qi >= p.Q) break;
 
     uint4 q[CH];
@@ -458,7 +507,7 @@ __global__ void __launch_bounds__(FNB_WARPS_PER_CTA * 32, fnb_min_ctas(CH)) fnb_
       for (uint32_t base = 0; base < p.nprobe; base += 32) {
         const uint32_t pi = base + lane;
         const bool valid = pi < p.nprobe;
-        const float d = batch_distance<DT, METRIC, G, CH, EXACT>(p, q, pi * p.step, valid, s_ids, lane, false);
+        const float d = batch_distance<DT, METRIC, G, CH, EXACT, UL>(p, q, pi * p.step, valid, s_ids, lane, false);
         if (valid) {
           const uint64_t k = ((uint64_t)ord_f32(d) << 32) | pi;
           best = k < best ? k : best;
@@ -483,6 +532,7 @@ __global__ void __launch_bounds__(FNB_WARPS_PER_CTA * 32, fnb_min_ctas(CH)) fnb_
       // ---- main loop (Index.h:627-658) ----
       for (;;) {
         uint32_t cur = FNB_EMPTY;
+        uint32_t spec = FNB_EMPTY;  // LAT: the runner-up candidate
         for (uint32_t base = start & ~31u; base < len; base += 32) {
           const uint32_t i = base + lane;
           const uint64_t e = (i < len) ? list[i] : 1ull;
@@ -495,7 +545,8 @@ __global__ void __launch_bounds__(FNB_WARPS_PER_CTA * 32, fnb_min_ctas(CH)) fnb_
             const unsigned b2 = b & (b - 1);
             if (b2) {  // runner-up: most likely the next node to be expanded
               const uint32_t id2 = __shfl_sync(FNB_FULL, (uint32_t)e, __ffs(b2) - 1) >> 1;
-              if (lane == 0) prefetch_l2(p.adj + (size_t)id2 * p.M);
+              if (LAT) spec = id2;
+              else if (lane == 0) prefetch_l2(p.adj + (size_t)id2 * p.M);
             }
             break;
           }
@@ -504,18 +555,34 @@ __global__ void __launch_bounds__(FNB_WARPS_PER_CTA * 32, fnb_min_ctas(CH)) fnb_
         __syncwarp();
         nhops++;
 
+        // LAT: the runner-up's first 32 links travel together with the current node's (its row was prefetched
+        // into L2 when it was a fresh neighbour)
+        uint32_t nb2 = spec;
+        if (LAT && spec != FNB_EMPTY && p.lines_per_row <= 8u && (uint32_t)lane < p.M)
+          nb2 = __ldg(p.adj + (size_t)spec * p.M + lane);
+
         for (uint32_t l0 = 0; l0 < p.M; l0 += 32) {
           uint32_t nb = cur;
           if (l0 + lane < p.M) nb = __ldg(p.adj + (size_t)cur * p.M + l0 + lane);
           // unused link slots are self-loops (Index.h:270): skip them without touching the visited set
           const bool fresh = (nb != cur) && visited_test_and_set(tab, p, nb);
           const unsigned fm = __ballot_sync(FNB_FULL, fresh);
+          if (LAT) {
+            if (fresh) {
+              const uint32_t* arow = p.adj + (size_t)nb * p.M;
+              for (uint32_t o = 0; o < p.M; o += 32) prefetch_l2(arow + o);
+            }
+            if (l0 == 0 && nb2 != spec && !visited_peek(tab, p, nb2)) {  // speculative: rows of the runner-up's links
+              const uint4* row = p.vec + (size_t)nb2 * p.stride;
+              for (uint32_t line = 0; line < p.lines_per_row; line++) prefetch_l2(row + line * 8u);
+            }
+          }
           if (!fm) continue;
           ndist += (uint32_t)__popc(fm);
           const bool full = len >= p.B;
           const uint32_t worst_hi = (uint32_t)(list[len - 1] >> 32);
 
-          const float d = batch_distance<DT, METRIC, G, CH, EXACT>(p, q, nb, fresh, s_ids, lane, true);
+          const float d = batch_distance<DT, METRIC, G, CH, EXACT, UL>(p, q, nb, fresh, s_ids, lane, !LAT || UL * (32 / G) < 32);
           const uint64_t key = make_key(d, nb);
           const bool acc = fresh && (!full || (uint32_t)(key >> 32) < worst_hi);
           if (!__any_sync(FNB_FULL, acc)) continue;
@@ -539,9 +606,12 @@ __global__ void __launch_bounds__(FNB_WARPS_PER_CTA * 32, fnb_min_ctas(CH)) fnb_
     if (lane == 0) {
       if (p.out_ndist) p.out_ndist[qi] = ndist;
       if (p.out_nhops) p.out_nhops[qi] = nhops;
-      atomicAdd(p.totals + 0, (unsigned long long)ndist);
-      atomicAdd(p.totals + 1, (unsigned long long)nhops);
-      if (len < p.K) atomicAdd(p.totals + 2, 1ull);
+      if (p.out_len) p.out_len[qi] = len < p.K ? len : p.K;
+      if (p.totals) {
+        atomicAdd(p.totals + 0, (unsigned long long)ndist);
+        atomicAdd(p.totals + 1, (unsigned long long)nhops);
+        if (len < p.K) atomicAdd(p.totals + 2, 1ull);
+      }
     }
     __syncwarp();
   }
@@ -591,23 +661,69 @@ inline void size_visited(SearchParams& p, int force_buckets, int min_ctas) {
   p.warp_smem = (list_bytes + buckets * 16u + 15u) & ~15u;
 }
 
+// The occupancy query and the shared-memory opt-in are per (device, kernel, shared-memory size): cached, because
+// the latency variant is launched once per query by search_single and every host microsecond counts there.
+struct LaunchCache {
+  size_t smem = ~(size_t)0;
+  int ctas_per_sm = 0;
+};
+
+template <typename Kern>
+static inline cudaError_t plan_launch(Kern kern, int threads, size_t smem, LaunchCache* cache, int* ctas_per_sm) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  LaunchCache& c = cache[dev & 15];
+  if (c.smem != smem) {
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int n = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, threads, smem);
+    if (e != cudaSuccess) return e;
+    c.ctas_per_sm = n;
+    c.smem = smem;
+  }
+  *ctas_per_sm = c.ctas_per_sm;
+  return c.ctas_per_sm < 1 ? cudaErrorLaunchOutOfResources : cudaSuccess;
+}
+
 template <int DT, int METRIC, int G, int CH>
 cudaError_t launch_search(const SearchParams& p, int num_sms, cudaStream_t stream) {
   const bool exact = p.nchunks == (uint32_t)(G * CH);
-  auto kern = exact ? fnb_search_kernel<DT, METRIC, G, CH, true> : fnb_search_kernel<DT, METRIC, G, CH, false>;
-  const size_t smem = (size_t)p.warp_smem * FNB_WARPS_PER_CTA;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
+  static LaunchCache cache[4][16];  // [exact][lat] x device; callers serialise launches per index, races only redo the query
   int ctas_per_sm = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, FNB_WARPS_PER_CTA * 32, smem);
+  if (p.lat) {
+    auto kern = exact ? fnb_search_kernel<DT, METRIC, G, CH, true, true> : fnb_search_kernel<DT, METRIC, G, CH, false, true>;
+    const size_t smem = (size_t)p.warp_smem;
+    cudaError_t e = plan_launch(kern, 32, smem, cache[exact ? 3 : 2], &ctas_per_sm);
+    if (e != cudaSuccess) return e;
+    long long grid = (long long)num_sms * ctas_per_sm;
+    if (grid > (long long)p.Q) grid = p.Q;
+    if (grid < 1) grid = 1;
+    kern<<<(unsigned)grid, 32, smem, stream>>>(p);
+    return cudaGetLastError();
+  }
+  auto kern = exact ? fnb_search_kernel<DT, METRIC, G, CH, true, false> : fnb_search_kernel<DT, METRIC, G, CH, false, false>;
+  const size_t smem = (size_t)p.warp_smem * FNB_WARPS_PER_CTA;
+  cudaError_t e = plan_launch(kern, FNB_WARPS_PER_CTA * 32, smem, cache[exact ? 1 : 0], &ctas_per_sm);
   if (e != cudaSuccess) return e;
-  if (ctas_per_sm < 1) return cudaErrorLaunchOutOfResources;
   long long grid = (long long)num_sms * ctas_per_sm;
   const long long need = ((long long)p.Q + FNB_WARPS_PER_CTA - 1) / FNB_WARPS_PER_CTA;
   if (grid > need) grid = need;
   if (grid < 1) grid = 1;
   kern<<<(unsigned)grid, FNB_WARPS_PER_CTA * 32, smem, stream>>>(p);
   return cudaGetLastError();
+}
+
+// Host rule for SearchParams::lat: the latency variant when every query of the batch can have a warp of its own on
+// a lightly loaded SM (<= 4 single-warp CTAs per SM).  FNB_LAT=0 / 1 forces the choice (tests, experiments).
+inline uint32_t choose_latency_variant(int64_t Q, int num_sms) {
+  static const int forced = [] {
+    const char* e = getenv("FNB_LAT");
+    return e ? atoi(e) : -1;
+  }();
+  if (forced >= 0) return forced ? 1u : 0u;
+  return Q <= 4ll * num_sms ? 1u : 0u;
 }
 
 }  // namespace fnb

@@ -150,6 +150,37 @@ static int do_search(char** a, int nargs) {
   return 0;
 }
 
+// Per-query latency of Index::search on one thread, the loop of experiments/run-benchmark.py:66-84
+// (search_single per query, wall clock around each call).  One untimed warm-up pass, then one timed pass.
+template <typename dist_t, typename elem_t>
+static int do_latency(char** a) {
+  std::string idx = a[0], qpath = a[1];
+  size_t Q = std::strtoull(a[2], nullptr, 10);
+  int K = std::atoi(a[3]), ef = std::atoi(a[4]), ninit = std::atoi(a[5]);
+  std::string out = a[6];
+  auto index = Index<dist_t, int>::loadIndex(idx);
+  size_t D = index->dataDimension();
+  auto qbuf = read_file(qpath, Q * D * sizeof(elem_t));
+  const elem_t* queries = reinterpret_cast<const elem_t*>(qbuf.data());
+  std::vector<double> lat(Q, 0.0);
+  size_t sink = 0;
+  for (int pass = 0; pass < 2; pass++) {
+    for (size_t i = 0; i < Q; i++) {
+      auto t0 = std::chrono::steady_clock::now();
+      auto r = index->search((const void*)(queries + i * D), K, ef, ninit);
+      lat[i] = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+      sink += r.size();
+    }
+  }
+  std::ofstream f(out, std::ios::binary);
+  f.write((const char*)lat.data(), (std::streamsize)(lat.size() * sizeof(double)));
+  double total = 0;
+  for (double v : lat) total += v;
+  std::printf("{\"op\":\"latency\",\"Q\":%zu,\"K\":%d,\"ef\":%d,\"mean_us\":%.3f,\"results\":%zu}\n", Q, K, ef,
+              Q ? total / (double)Q * 1e6 : 0.0, sink);
+  return 0;
+}
+
 template <typename dist_t>
 static int do_reorder(char** a) {
   auto index = Index<dist_t, int>::loadIndex(a[0]);
@@ -197,6 +228,7 @@ template <typename dist_t, typename elem_t>
 static int run(const std::string& op, DataType dt, char** a, int n) {
   if (op == "build" && n >= 7) return do_build<dist_t, elem_t>(dt, a, n);
   if (op == "search" && n >= 9) return do_search<dist_t, elem_t>(a, n);
+  if (op == "latency" && n >= 7) return do_latency<dist_t, elem_t>(a);
   if (op == "info" && n >= 1) return do_info<dist_t>(a);
   if (op == "reorder" && n >= 3) return do_reorder<dist_t>(a);
   if (op == "mtx" && n >= 6) return do_mtx<dist_t, elem_t>(dt, a);
@@ -206,7 +238,7 @@ static int run(const std::string& op, DataType dt, char** a, int n) {
 
 int main(int argc, char** argv) {
   if (argc < 4) {
-    std::fprintf(stderr, "usage: ref_flatnav build|search|info <l2|ip> <f32|u8|i8> ...\n");
+    std::fprintf(stderr, "usage: ref_flatnav build|search|latency|info <l2|ip> <f32|u8|i8> ...\n");
     return 2;
   }
   std::string op = argv[1], metric = argv[2], dtype = argv[3];

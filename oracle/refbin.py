@@ -90,6 +90,20 @@ def search(index_path: str, metric: str, queries: np.ndarray, K: int, ef: int, n
     return d, l, info
 
 
+def latency(index_path: str, metric: str, queries: np.ndarray, K: int, ef: int, ninit: int = 100,
+            timeout: float | None = None) -> np.ndarray:
+    """Per-query wall-clock seconds of Index::search on one thread (the search_single loop of
+    experiments/run-benchmark.py:66-84), measured inside the reference process after one warm-up pass."""
+    queries = np.ascontiguousarray(queries)
+    Q = queries.shape[0]
+    with tempfile.TemporaryDirectory() as td:
+        qp, op = os.path.join(td, "q.bin"), os.path.join(td, "lat.bin")
+        queries.tofile(qp)
+        _run(["latency", metric, DT[queries.dtype], index_path, qp, str(Q), str(K), str(ef), str(ninit), op],
+             timeout=timeout)
+        return np.fromfile(op, dtype=np.float64)
+
+
 def reorder(index_path: str, metric: str, dtype: str, strategies, out_path: str, timeout: float | None = None) -> dict:
     """Index::loadIndex + doGraphReordering(strategies) + saveIndex with the reference itself (Index.h:412-427).
     `dtype` is "f32", "u8" or "i8"."""
