@@ -93,6 +93,50 @@ int main(int argc, char** argv) {
     r->saveIndex(out + ".rcm_gorder.idx");
   }
 
+  // construction through the shim, the way tools/construct_npy.cpp:37-54,78-80 builds an index: distance object ->
+  // constructor -> addBatch -> saveIndex; then every inserted vector must find itself (distance 0, its label)
+  {
+    using flatnav::distances::InnerProductDistance;
+    const int M = 16;
+    auto distance = SquaredL2Distance<>::create(D);
+    if (distance->dimension() != D || distance->dataSize() != 4 * D) return 30;
+    Index<SquaredL2Distance<DataType::float32>, int> built(std::move(distance), (int)Q + 1, M, /*collect_stats=*/true);
+    if (built.currentNumNodes() != 0 || built.maxNodeCount() != Q + 1 || built.maxEdgesPerNode() != (size_t)M) return 31;
+    std::vector<int> labels(Q);
+    for (size_t i = 0; i < Q; i++) labels[i] = 1000 + (int)i;
+    try {
+      built.addBatch<float>(q.data(), labels, 64, 0);
+      return 32;
+    } catch (const std::invalid_argument&) { checks++; }  // Index.h:303-305
+    built.addBatch<float>(q.data(), labels, 64);
+    if (built.currentNumNodes() != Q) return 33;
+    int one = 7777;
+    uint32_t nid = 0;
+    std::vector<float> far(D, 1e3f);
+    built.allocateNode(far.data(), one, nid);  // Index.h:262-272: unlinked, unreachable from the graph
+    if (nid != Q || built.currentNumNodes() != Q + 1) return 34;
+    try {
+      built.add(far.data(), one, 64, 100);
+      return 35;
+    } catch (const std::runtime_error&) { checks++; }  // Index.h:353-357: index full
+    size_t self = 0;
+    for (size_t i = 0; i < Q; i++) {
+      auto r = built.search(q.data() + i * D, 1, 64);
+      if (r.size() == 1 && r[0].second == 1000 + (int)i && r[0].first == 0.0f) self++;
+    }
+    if (self * 100 < Q * 95) return 36;
+    if (built.distanceComputations() == 0 || built.metricHops() == 0) return 37;  // collect_stats (Index.h:529)
+    built.resetStats();
+    if (built.distanceComputations() != 0) return 38;
+    built.getIndexSummary();  // Index.h:538-547
+    built.saveIndex(out + ".built.idx");
+    auto reloaded = Index<SquaredL2Distance<DataType::float32>, int>::loadIndex(out + ".built.idx");
+    if (reloaded->currentNumNodes() != Q + 1 || reloaded->maxEdgesPerNode() != (size_t)M) return 39;
+    auto a = built.search(q.data(), 5, 32), b = reloaded->search(q.data(), 5, 32);
+    if (a != b) return 40;
+    if (reloaded->distanceComputations() != 0) return 41;  // a loaded index does not collect stats
+  }
+
   auto moved = std::move(*index);  // move-only ownership (Index.h:86-132)
   if (moved.currentNumNodes() == 0) return 20;
 

@@ -292,7 +292,8 @@ def test_cpp_shim_end_to_end(tmp_path):
     r = subprocess.run([exe, golden_index_path(case["name"]), qp, str(g["queries"].shape[0]), str(K), str(ef), out],
                        capture_output=True, text=True)
     assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
-    assert "shim ok, 5 exception checks" in r.stdout
+    assert "shim ok, 7 exception checks" in r.stdout
+    assert "max_edges_per_node (M): 16" in r.stdout and "cur_num_nodes:" in r.stdout  # getIndexSummary
     import hashlib
     import json
     want = json.load(open(os.path.join(ROOT, "tests", "golden", "reorder.json")))["reorder"][case["name"]]["rcm,gorder"]
