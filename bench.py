@@ -153,7 +153,7 @@ def run_reference(args, rank: int, world: int) -> None:
     from tools.workload import ensure_index
     w = WORKLOAD
     if not refbin.available():
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref reference binary cannot run on this host"}))
+        emit({"impl": "reference", "unavailable": "oracle/_ref reference binary cannot run on this host"})
         return
     path, _ = ensure_index(w["gen"], w["n"], w["dim"], w["metric"], w["M"], w["efc"], builder=w.get("builder", "reference"))
     cores = os.cpu_count() or 1
@@ -175,10 +175,31 @@ def run_reference(args, rank: int, world: int) -> None:
         "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------------
+_RESULT_FD = None
+
+
+def claim_stdout() -> None:
+    """stdout carries exactly ONE line, the result: everything else a library prints there from native code (NCCL's
+    version banner under torchrun, for one) is sent to stderr for the length of the run."""
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
+
+
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -188,6 +209,7 @@ def main() -> None:
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     apply_env_overrides()
+    claim_stdout()
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
 
     if args.impl == "reference":
@@ -308,7 +330,7 @@ def main() -> None:
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(path, batches[0])
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

@@ -50,6 +50,7 @@ def main():
     torch.cuda.set_device(local)
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     os.environ.setdefault("MASTER_PORT", "29533")
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
 
     cls = {"latent-u8": flatnav_b200.index.IndexL2Uint8, "latent": flatnav_b200.index.IndexL2Float,
