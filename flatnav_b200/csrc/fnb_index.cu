@@ -253,7 +253,8 @@ static int build_index(const unsigned char* file, size_t nbytes, int metric, int
 }
 
 // ---- search dispatch ---------------------------------------------------------------------------------
-int plan_search(const fnb_index* ix, int64_t Q, int K, int ef, int ninit, SearchParams* p) {
+// launch_q: queries per kernel launch (the occupancy plan depends on it); <= 0 means Q
+int plan_search(const fnb_index* ix, int64_t Q, int K, int ef, int ninit, SearchParams* p, int64_t launch_q) {
   if (Q < 0) return fail(FNB_ERR_INVALID_ARG, "negative query count");
   if (K <= 0) return fail(FNB_ERR_INVALID_ARG, "K must be positive");
   if (ninit <= 0) return fail(FNB_ERR_INVALID_ARG, "num_initializations must be greater than 0.");
@@ -279,7 +280,11 @@ int plan_search(const fnb_index* ix, int64_t Q, int K, int ef, int ninit, Search
   while (p->Bpow2 * 2u <= p->Bcap) p->Bpow2 *= 2u;
   p->lines_per_row = (ix->stride * FNB_CHUNK_BYTES + 127u) / 128u;
   const char* env = getenv("FNB_VS_BUCKETS");  // development / test knob: visited-set buckets per query
-  size_visited(*p, env ? atoi(env) : 0, fnb_min_ctas(fnb_chunks_per_lane(ix->nchunks, ix->G)));
+  const int cpl = fnb_chunks_per_lane(ix->nchunks, ix->G);
+  const int sms = ix->replicas.empty() ? 148 : ix->replicas[0].num_sms;
+  if (launch_q <= 0) launch_q = Q;
+  p->dense = choose_latency_variant(launch_q, sms) ? 0u : choose_dense_plan(launch_q, sms, ix->G, cpl, p->B);
+  size_visited(*p, env ? atoi(env) : 0, p->dense ? FNB_CTAS_DENSE : fnb_min_ctas(cpl));
   if ((uint64_t)p->warp_smem * FNB_WARPS_PER_CTA > 227u * 1024u)
     return fail(FNB_ERR_UNSUPPORTED, "ef_search=%d needs %u bytes of shared memory per query; limit is %u", ef,
                 p->warp_smem, 227u * 1024u / FNB_WARPS_PER_CTA);
@@ -474,7 +479,8 @@ int fnb_search(fnb_index* ix, const void* queries, int64_t Q, int K, int ef_sear
                float* out_dist, int32_t* out_label, fnb_search_stats* stats) {
   if (!ix) return fail(FNB_ERR_INVALID_ARG, "index is NULL");
   SearchParams p0;
-  int rc = plan_search(ix, Q, K, ef_search, num_initializations, &p0);
+  const int64_t n_rep = ix->replicas.empty() ? 1 : (int64_t)ix->replicas.size();
+  int rc = plan_search(ix, Q, K, ef_search, num_initializations, &p0, (Q + n_rep - 1) / n_rep);
   if (rc != FNB_OK) return rc;
   if (stats) memset(stats, 0, sizeof(*stats));
   if (Q == 0) return FNB_OK;

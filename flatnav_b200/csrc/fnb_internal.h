@@ -60,7 +60,7 @@ int upload_new_rows_locked(fnb_index* ix, const void* vectors, const int32_t* la
                            bool init_links);
 
 namespace fnb {
-int plan_search(const fnb_index* ix, int64_t Q, int K, int ef, int ninit, SearchParams* p);
+int plan_search(const fnb_index* ix, int64_t Q, int K, int ef, int ninit, SearchParams* p, int64_t launch_q = 0);
 cudaError_t dispatch_search(const fnb_index* ix, const SearchParams& p, int num_sms, cudaStream_t s);
 cudaError_t dispatch_search_f32(const fnb_index* ix, const SearchParams& p, int num_sms, cudaStream_t s);
 cudaError_t dispatch_search_u8(const fnb_index* ix, const SearchParams& p, int num_sms, cudaStream_t s);

@@ -54,6 +54,11 @@ enum { M_L2 = 0, M_IP = 1 };
 __host__ __device__ constexpr int fnb_min_ctas(int ch) {
   return ch <= 1 ? FNB_CTAS_TINY_ROWS : (ch <= 4 ? FNB_CTAS_SHORT_ROWS : (ch <= 8 ? 4 : 3));
 }
+// Dense plan for LARGE batches of short rows: 7 CTAs = 28 warps per SM (72 registers per thread).  Measured on 100k-query
+// batches: +6 ... +11 % QPS over the 24-warp plan on every short-row configuration.  On a batch of a few waves (10k
+// queries are 2.8 waves of 3552 warps) the last, partly filled wave costs more with more slots than the extra
+// residency earns, so the host picks the plan per launch from the batch size (choose_dense_plan).
+#define FNB_CTAS_DENSE 7
 __host__ __device__ constexpr int fnb_batches_in_flight(int ch) { return ch >= 4 ? 1 : 4 / ch; }
 // Latency variant (few queries, one warp per CTA, registers are free): hold as many warp-wide load batches in
 // registers as ~96 staging registers allow, up to all 32 rows of an expansion, so that one hop costs ONE HBM round
@@ -88,6 +93,7 @@ struct SearchParams {
   uint32_t query_vec_ok;  // 1 => query rows are 16-byte aligned and a whole number of chunks
   uint32_t query_pitch_chunks;  // != 0 => queries are rows of a padded vector array with this pitch (construction:
                                 // the new nodes' own rows); chunks beyond the data are zero there
+  uint32_t dense;  // 1 => the 28-warps-per-SM instantiation (large batches of short rows; never with lat)
   uint32_t lat;  // 1 => latency variant (few queries): one warp per CTA, query = blockIdx.x (grid-stride), `counter` unused
 };
 
@@ -467,8 +473,8 @@ __device__ __forceinline__ void merge_accepted(volatile uint64_t* list, uint32_t
 //   * speculation that cannot change the result: while the current node's rows are in flight, the links of the
 //     runner-up candidate (the most likely next expansion) are read, filtered through the visited set READ-ONLY, and
 //     their vector rows prefetched into L2.
-template <int DT, int METRIC, int G, int CH, bool EXACT, bool LAT>
-__global__ void __launch_bounds__(LAT ? 32 : FNB_WARPS_PER_CTA * 32, LAT ? 1 : fnb_min_ctas(CH))
+template <int DT, int METRIC, int G, int CH, bool EXACT, bool LAT, int OCC = 0>
+__global__ void __launch_bounds__(LAT ? 32 : FNB_WARPS_PER_CTA * 32, LAT ? 1 : (OCC > 0 ? OCC : fnb_min_ctas(CH)))
     fnb_search_kernel(const SearchParams p) {
   extern __shared__ __align__(16) unsigned char fnb_smem[];
   const int lane = threadIdx.x & 31;
@@ -690,7 +696,7 @@ static inline cudaError_t plan_launch(Kern kern, int threads, size_t smem, Launc
 template <int DT, int METRIC, int G, int CH>
 cudaError_t launch_search(const SearchParams& p, int num_sms, cudaStream_t stream) {
   const bool exact = p.nchunks == (uint32_t)(G * CH);
-  static LaunchCache cache[4][16];  // [exact][lat] x device; callers serialise launches per index, races only redo the query
+  static LaunchCache cache[6][16];  // [exact][lat | dense] x device; callers serialise launches per index, races only redo the query
   int ctas_per_sm = 0;
   if (p.lat) {
     auto kern = exact ? fnb_search_kernel<DT, METRIC, G, CH, true, true> : fnb_search_kernel<DT, METRIC, G, CH, false, true>;
@@ -704,8 +710,16 @@ cudaError_t launch_search(const SearchParams& p, int num_sms, cudaStream_t strea
     return cudaGetLastError();
   }
   auto kern = exact ? fnb_search_kernel<DT, METRIC, G, CH, true, false> : fnb_search_kernel<DT, METRIC, G, CH, false, false>;
+  LaunchCache* lc = cache[exact ? 1 : 0];
+  if constexpr (CH <= 4 && G <= 8) {
+    if (p.dense) {
+      kern = exact ? fnb_search_kernel<DT, METRIC, G, CH, true, false, FNB_CTAS_DENSE>
+                   : fnb_search_kernel<DT, METRIC, G, CH, false, false, FNB_CTAS_DENSE>;
+      lc = cache[exact ? 5 : 4];
+    }
+  }
   const size_t smem = (size_t)p.warp_smem * FNB_WARPS_PER_CTA;
-  cudaError_t e = plan_launch(kern, FNB_WARPS_PER_CTA * 32, smem, cache[exact ? 1 : 0], &ctas_per_sm);
+  cudaError_t e = plan_launch(kern, FNB_WARPS_PER_CTA * 32, smem, lc, &ctas_per_sm);
   if (e != cudaSuccess) return e;
   long long grid = (long long)num_sms * ctas_per_sm;
   const long long need = ((long long)p.Q + FNB_WARPS_PER_CTA - 1) / FNB_WARPS_PER_CTA;
@@ -713,6 +727,30 @@ cudaError_t launch_search(const SearchParams& p, int num_sms, cudaStream_t strea
   if (grid < 1) grid = 1;
   kern<<<(unsigned)grid, FNB_WARPS_PER_CTA * 32, smem, stream>>>(p);
   return cudaGetLastError();
+}
+
+// Host rule for SearchParams::dense.  Both plans keep persistent warps pulling queries, so a launch lasts about
+// waves(c) = Q / slots(c) "rounds" of slots(c) / throughput(c) each, and its last round is only partly filled; the
+// measured cost of that tail is about half of what idle slots would suggest (the busy warps of a thin round run faster).
+// throughput(7 CTAs) = 1.08 x throughput(6 CTAs) on full waves (tools/ab_probe.py, 100k-query batches).  The dense
+// plan is taken when it wins by 2 % or more: never at 10k queries (2.8 vs 2.4 waves), from ~16k queries on always.
+// FNB_DENSE=0 / 1 forces the choice (tests, experiments).
+inline uint32_t choose_dense_plan(int64_t Q, int num_sms, int lanes_per_row, int chunks_per_lane, uint32_t B) {
+  static const int forced = [] {
+    const char* e = getenv("FNB_DENSE");
+    return e ? atoi(e) : -1;
+  }();
+  // rows above 512 B keep their own plans (more registers per lane); long lists need the shared memory
+  if (lanes_per_row > 8 || chunks_per_lane > 4 || B > 256u) return 0u;
+  if (forced >= 0) return forced ? 1u : 0u;
+  auto cost = [&](int ctas, double thr) {
+    const double slots = (double)num_sms * ctas * FNB_WARPS_PER_CTA;
+    const double waves = (double)Q / slots;
+    double whole = (double)(long long)waves;
+    if (whole < waves) whole += 1.0;
+    return (waves + 0.5 * (whole - waves)) * slots / thr;
+  };
+  return cost(FNB_CTAS_DENSE, 1.08) < 0.98 * cost(fnb_min_ctas(chunks_per_lane), 1.0) ? 1u : 0u;
 }
 
 // Host rule for SearchParams::lat: the latency variant when every query of the batch can have a warp of its own on

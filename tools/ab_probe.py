@@ -4,6 +4,7 @@ same graphs and queries, one subprocess per build (FNB_LIB_PATH), and check that
 
     python tools/ab_probe.py --libs base=flatnav_b200/libflatnav_b200.so,spec=variants/libspec.so \
         --cases cfg1,cfg2,u8 --out gpurun_out/ab.json
+    python tools/ab_probe.py --libs auto=flatnav_b200/libflatnav_b200.so,sparse=flatnav_b200/libflatnav_b200.so@FNB_DENSE=0 ...
 
 Graphs are built on the GPU by the default library (seconds) and cached under data_cache/.
 """
@@ -26,6 +27,10 @@ CASES = {
     "cfg2": dict(gen="latent-norm", n=1_200_000, dim=100, metric="ip", K=10, efs=[32, 64, 128, 256], Q=10_000),
     "cfg3s": dict(gen="latent", n=4_000_000, dim=96, metric="l2", K=10, efs=[64, 100], Q=50_000),
     "cfg4s": dict(gen="latent", n=400_000, dim=960, metric="l2", K=100, efs=[100, 300], Q=5_000, rank=32),
+    # large batches: the tail of the last wave of queries no longer matters (occupancy experiments)
+    "cfg1big": dict(gen="latent", n=1_000_000, dim=128, metric="l2", K=10, efs=[64, 100, 200], Q=100_000),
+    "cfg2big": dict(gen="latent-norm", n=1_200_000, dim=100, metric="ip", K=10, efs=[64, 128], Q=100_000),
+    "u8big": dict(gen="latent-u8", n=4_000_000, dim=128, metric="l2", K=10, efs=[64, 100], Q=100_000),
     "u8": dict(gen="latent-u8", n=4_000_000, dim=128, metric="l2", K=10, efs=[32, 64, 100, 200], Q=10_000),
 }
 
@@ -87,7 +92,9 @@ def main() -> None:
         path, binfo = ensure_index(c["gen"], c["n"], c["dim"], c["metric"], 32, 100, rank=c.get("rank", 16), builder="gpu")
         result[case] = {"build": binfo, "libs": {}}
         for name, lp in libs:
+            lp, *assign = lp.split("@")  # path@VAR=VALUE@...: the same build under different environment knobs
             env = dict(os.environ, FNB_LIB_PATH=os.path.join(ROOT, lp))
+            env.update(kv.split("=", 1) for kv in assign)
             r = subprocess.run([sys.executable, os.path.abspath(__file__), "--libs", "x=x", "--reps", str(args.reps),
                                 "--child", case, path], env=env, capture_output=True, text=True)
             rows = None
