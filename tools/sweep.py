@@ -54,6 +54,8 @@ def main():
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--no-ref", action="store_true")
     ap.add_argument("--ref-sample", type=int, default=2000)
+    ap.add_argument("--builder", default="reference", choices=["reference", "gpu"],
+                    help="who builds the graph when it is not cached: the unmodified reference, or this engine's GPU construction")
     args = ap.parse_args()
     c = dict(CONFIGS[args.config])
     if args.n:
@@ -70,7 +72,7 @@ def main():
 
     kw = {"rank": c["rank"]} if "rank" in c else {}
     t0 = time.time()
-    path, binfo = ensure_index(c["gen"], c["n"], c["dim"], c["metric"], c["M"], c["efc"], **kw)
+    path, binfo = ensure_index(c["gen"], c["n"], c["dim"], c["metric"], c["M"], c["efc"], builder=args.builder, **kw)
     print(f"[sweep] index ready in {time.time() - t0:.1f}s: {binfo}", flush=True)
     q = synthetic.make(c["gen"], c["Q"], c["dim"], queries=True, **kw)
     cls = getattr(flatnav_b200.index, CLS[(c["metric"], q.dtype.name)])
