@@ -113,6 +113,24 @@ def test_cuda_vs_live_reference_and_oracle(ref_cache, metric, gen, dim, n, M):
             assert abs(recall(l, gt_l) - recall(lr, gt_l)) <= 0.002
 
 
+def test_large_batch_takes_the_dense_plan_and_changes_nothing(ref_cache):
+    """A batch of many waves is launched with the 28-warps-per-SM instantiation (choose_dense_plan): the results must be
+    the bytes the 24-warp plan returns for the same queries in small batches, and the oracle's on a sample."""
+    path = build_ref_index(ref_cache, "l2", "latent", 20000, 128, 32, 100)
+    q = synthetic.make("latent", 40000, 128, queries=True)
+    ix = flatnav_b200.index.IndexL2Float.load_index(path)
+    d, l = ix.search(q, 10, 64)              # 40000 queries: ~10 waves -> dense plan
+    big = dict(ix.last_stats)
+    parts = [ix.search(q[i:i + 5000], 10, 64) for i in range(0, len(q), 5000)]   # 1.4 waves each -> default plan
+    np.testing.assert_array_equal(d.view(np.uint32), np.concatenate([p[0] for p in parts]).view(np.uint32))
+    np.testing.assert_array_equal(l, np.concatenate([p[1] for p in parts]))
+    assert big["n_queries"] == 40000
+    ora = port.OracleIndex(path, port.L2)
+    do, lo = ora.search(q[:500], 10, 64, mode=port.MODE_LIST)
+    np.testing.assert_array_equal(d[:500].view(np.uint32), do.view(np.uint32))
+    np.testing.assert_array_equal(l[:500], lo)
+
+
 def test_tiny_visited_set_and_large_ef(ref_cache):
     """a deliberately tiny visited set forgets constantly: results must not change, only n_dist grows"""
     path = build_ref_index(ref_cache, "l2", "latent", 20000, 128, 32, 100)

@@ -108,7 +108,8 @@ def full(tag, rep, name="search_kernel", traffic_json=True):
         f.write(f"# {tag}: hottest source lines of {vals[hdr0.index('Kernel Name')][:90]} (ncu --set full --import-source on; -lineinfo)\n\n"
                 f"total warp-instructions attributed: {ti}, stall samples: {ts}\n\n"
                 "| line | % instructions | % stall samples | source |\n|---:|---:|---:|---|\n")
-        for ln, s, i, sa in sorted(lines, key=lambda x: -x[2])[:30]:
+        by = 3 if "--by-samples" in sys.argv else 2  # latency-bound kernels: rank by stall samples instead
+        for ln, s, i, sa in sorted(lines, key=lambda x: -x[by])[:40 if by == 3 else 30]:
             f.write(f"| {ln} | {100 * i / ti:.1f} | {100 * sa / ts:.1f} | `{s[:110]}` |\n")
 
 
