@@ -413,27 +413,50 @@ __device__ __forceinline__ void visited_clear(uint32_t* tab, uint32_t buckets, i
 __device__ __forceinline__ void merge_accepted(volatile uint64_t* list, uint32_t& len, uint32_t& start,
                                                const uint32_t B, const uint32_t Bpow2, const uint64_t key, bool acc,
                                                const int lane) {
-  // lower_bound(list[0..len), key) ignoring the expanded bit
+  // lower_bound(list[0..len), key) ignoring the expanded bit.  Binary search on the DISTANCE word alone: 32-bit loads
+  // and compares, the load unconditional through a clamped index, so the loop body is straight-line code.  Only when a
+  // lane lands on an entry with its own distance word (an exact distance tie, or a node the visited set forgot) is
+  // the search repeated with the full (distance, id) keys.
+  const uint32_t khi = (uint32_t)(key >> 32);
+  const volatile uint32_t* l32 = reinterpret_cast<const volatile uint32_t*>(list);  // word 2i+1 = distance of entry i
   uint32_t lo = 0;
   for (uint32_t step = Bpow2; step; step >>= 1) {
     const uint32_t idx = lo + step;
-    if (idx <= len && (list[idx - 1] & ~1ull) < key) lo = idx;
+    const uint32_t j = min(idx, len);  // len >= 1: the entry node is in the list before the first merge
+    if ((l32[2u * j - 1u] < khi) & (idx <= len)) lo = idx;
   }
-  if (lo < len && (list[lo] & ~1ull) == key) acc = false;  // already in the list
+  const bool tie = acc && lo < len && l32[2u * lo + 1u] == khi;
+  if (__any_sync(FNB_FULL, tie)) {
+    lo = 0;
+    for (uint32_t step = Bpow2; step; step >>= 1) {
+      const uint32_t idx = lo + step;
+      if (idx <= len && (list[idx - 1] & ~1ull) < key) lo = idx;
+    }
+    if (lo < len && (list[lo] & ~1ull) == key) acc = false;  // already in the list
+  }
   unsigned am = __ballot_sync(FNB_FULL, acc);
   uint32_t rank = 0;
-  bool dup = false;
-  for (unsigned m = am; m; m &= m - 1) {
-    const int s = __ffs(m) - 1;
-    const uint64_t kj = shfl64(key, s);
-    rank += (kj < key) ? 1u : 0u;
-    dup |= (kj == key) && (s < lane);
-  }
-  if (__any_sync(FNB_FULL, acc && dup)) {  // a link listed twice: keep the lowest lane, redo the ranks
-    acc = acc && !dup;
-    am = __ballot_sync(FNB_FULL, acc);
-    rank = 0;
-    for (unsigned m = am; m; m &= m - 1) rank += (shfl64(key, __ffs(m) - 1) < key) ? 1u : 0u;
+  if (am & (am - 1u)) {  // two or more accepted: rank each among the others
+    // Candidates of one expansion rarely share a distance word; then 32-bit compares rank them and no link can be
+    // listed twice among them.  match.any groups the accepted lanes by distance word in one instruction.
+    const unsigned peers = __match_any_sync(FNB_FULL, acc ? khi : ~(uint32_t)lane) & am;
+    if (!__any_sync(FNB_FULL, acc && peers != (1u << lane))) {
+      for (unsigned m = am; m; m &= m - 1) rank += (__shfl_sync(FNB_FULL, khi, __ffs(m) - 1) < khi) ? 1u : 0u;
+    } else {
+      bool dup = false;
+      for (unsigned m = am; m; m &= m - 1) {
+        const int s = __ffs(m) - 1;
+        const uint64_t kj = shfl64(key, s);
+        rank += (kj < key) ? 1u : 0u;
+        dup |= (kj == key) && (s < lane);
+      }
+      if (__any_sync(FNB_FULL, acc && dup)) {  // a link listed twice: keep the lowest lane, redo the ranks
+        acc = acc && !dup;
+        am = __ballot_sync(FNB_FULL, acc);
+        rank = 0;
+        for (unsigned m = am; m; m &= m - 1) rank += (shfl64(key, __ffs(m) - 1) < key) ? 1u : 0u;
+      }
+    }
   }
   if (!am) return;
   const uint32_t n_acc = (uint32_t)__popc(am);
