@@ -79,6 +79,7 @@ LIVE = [
     ("l2", "latent", 128, 20000, 32), ("ip", "latent-norm", 100, 12000, 32), ("l2", "latent", 96, 12000, 32),
     ("l2", "latent-u8", 128, 20000, 32), ("ip", "latent-i8", 64, 8000, 16), ("l2", "latent", 960, 4000, 32),
     ("l2", "iid", 500, 3000, 16), ("l2", "latent-i8", 100, 8000, 40),
+    ("ip", "latent-norm", 256, 5000, 24),  # 64 chunks: the exact-fit 32-lane instantiation (no per-chunk predicates)
 ]
 
 
