@@ -14,6 +14,7 @@ Beside it: the unmodified reference (oracle/_ref) doing the same loop on one hos
 process (no Python in its numbers), and this engine's batched `search` over the same queries for contrast.
 
     python tools/latency.py [cfg1] [--q 2000] [--efs 32,64,100,200] [--out profiles/r1_latency_cfg1.json]
+    python tools/latency.py cfg1 --paper       # k = 100 and the authors' ef_search list
 """
 from __future__ import annotations
 
@@ -71,7 +72,14 @@ def main() -> None:
     ap.add_argument("--out", default=None)
     ap.add_argument("--no-ref", action="store_true")
     ap.add_argument("--builder", default="reference")
+    ap.add_argument("--k", type=int, default=0, help="override the config's K")
+    ap.add_argument("--paper", action="store_true",
+                    help="the authors' settings (experiments/Makefile:8-22, run-benchmark.py:44): k = 100, "
+                         "ef_search in {100, 200, 300, 500, 1000, 3000}")
     args = ap.parse_args()
+    if args.paper:
+        args.k = args.k or 100
+        args.efs = "100,200,300,500,1000,3000"
 
     import flatnav_b200
     from flatnav_b200 import synthetic
@@ -86,7 +94,7 @@ def main() -> None:
     queries = synthetic.make(c["gen"], args.q, c["dim"], queries=True, rank=rank)
     cls = getattr(flatnav_b200.index, CLS[(c["metric"], queries.dtype.name)])
     ix = cls.load_index(path, devices=[0])
-    K = c["K"]
+    K = args.k or c["K"]
     _, gt = ix.bruteforce(queries, K)
     for q in queries[:200]:  # warm-up: context, workspace, clocks
         ix.search_single(q, K, 64)
