@@ -118,7 +118,7 @@ def main() -> None:
             row["reference_1thread"] = summarize(lat)
         rows.append(row)
         print(json.dumps(row), flush=True)
-    out = {"config": args.config, "params": {k: v for k, v in c.items() if k != "efs"}, "num_queries": args.q,
+    out = {"config": args.config, "params": dict({k: v for k, v in c.items() if k != "efs"}, K=K), "num_queries": args.q,
            "protocol": "experiments/run-benchmark.py compute_metrics: search_single per query, time.time() around each call",
            "host_cores": os.cpu_count(), "reference_isa": refbin.isa(), "index_build": binfo, "rows": rows}
     if args.out:
