@@ -1,7 +1,8 @@
 """Benchmark / test infrastructure (NOT part of the product package): materialise a synthetic dataset and an
-index file for it.  Index CONSTRUCTION is outside the hot path flatnav_b200 replaces (component
-#10), so the graph is built by the unmodified reference (oracle/_ref/ref_flatnav_*: Index::addBatch +
-saveIndex) and cached under data_cache/ keyed by every parameter that shapes it."""
+index file for it, cached under data_cache/ keyed by every parameter that shapes it.  Two builders write the same
+file format: the unmodified reference (oracle/_ref/ref_flatnav_*: Index::addBatch + saveIndex) and this engine's own
+GPU construction (csrc/build.cu).  `cached_index` only looks: the product arm of bench.py uses it to search the very
+file the reference arm built when that is there, and builds its own otherwise, without running anything under oracle/."""
 from __future__ import annotations
 
 import json
@@ -21,13 +22,23 @@ def index_name(gen: str, n: int, dim: int, metric: str, M: int, efc: int, rank: 
     return f"{gen}{r}_n{n}_d{dim}_{metric}_M{M}_efc{efc}_seed42"
 
 
+def cached_index(gen: str, n: int, dim: int, metric: str, M: int = 32, efc: int = 100, rank: int = 16, builder: str = "reference"):
+    """(path, info) of an index file already in the cache, else None.  Never builds, never imports oracle/."""
+    path = os.path.join(CACHE, index_name(gen, n, dim, metric, M, efc, rank) + ("_gpubuilt" if builder == "gpu" else "") + ".idx")
+    meta = path + ".json"
+    if os.path.exists(path) and os.path.exists(meta):
+        info = json.load(open(meta))
+        info["cached"] = True
+        return path, info
+    return None
+
+
 def ensure_index(gen: str, n: int, dim: int, metric: str, M: int = 32, efc: int = 100, threads: int = 0,
                  rank: int = 16, builder: str = "reference"):
     """Return (path, info).  Builds the file if it is not cached: with the reference binary (default), or with this
     engine's GPU construction (builder="gpu": the large configs, where the CPU build takes minutes) — either way the
     file is in the reference's format and both arms of a benchmark read the same graph."""
     from flatnav_b200 import synthetic
-    from oracle import refbin
     os.makedirs(CACHE, exist_ok=True)
     path = os.path.join(CACHE, index_name(gen, n, dim, metric, M, efc, rank) + ("_gpubuilt" if builder == "gpu" else "") + ".idx")
     meta = path + ".json"
@@ -54,6 +65,7 @@ def ensure_index(gen: str, n: int, dim: int, metric: str, M: int = 32, efc: int 
                 "gen_seconds": round(t_gen, 2), "builder": "flatnav_b200 GPU construction", "cached": False}
         json.dump(info, open(meta, "w"))
         return path, info
+    from oracle import refbin  # only the reference builder touches oracle/
     if not refbin.available():
         raise RuntimeError("no cached index and the reference builder (oracle/_ref) cannot run on this host")
     t0 = time.time()
