@@ -6,7 +6,7 @@ unmodified reference's QPS on this host's cores (oracle/_ref, bounded sample).
 
     python tools/sweep.py cfg2 [--out profiles/r1_sweep_cfg2.json] [--n N] [--q Q] [--no-ref]
 
-The graph is built by the unmodified reference (construction is out of scope) and cached under data_cache/.
+The graph is built by the unmodified reference (default) or by this engine (--builder gpu) and cached under data_cache/.
 """
 from __future__ import annotations
 
