@@ -145,20 +145,25 @@ static Csr in_table(const Csr& out, uint32_t n) {
 // entry of priority pm lowers the true value of every p > pm from size to size - 1, which the clamp delivers
 // without touching the table (for p <= pm the popped entry was not counted, and lo[p] <= size - 1 already).
 struct GorderQueue {
-  std::vector<int32_t> pos;      // key -> slot, -1 once popped
-  std::vector<int32_t> prio;     // key -> priority
+  struct State {
+    int32_t pos;   // key -> slot, -1 once popped
+    int32_t prio;  // key -> priority
+  };
+  std::vector<State> st;         // one cache line access per key for both fields
   std::vector<uint32_t> key_at;  // slot -> key
   std::vector<uint32_t> lo;      // boundary table, indexed by priority + kOff
   uint32_t size, n;
   static constexpr int32_t kOff = 4;  // priorities never go negative (every decrement undoes an increment of a
                                       // key that was already live then); the offset is a safety margin only
-  explicit GorderQueue(uint32_t n_) : pos(n_), prio(n_, 0), key_at(n_), lo(64, n_), size(n_), n(n_) {
+  explicit GorderQueue(uint32_t n_) : st(n_), key_at(n_), lo(64, n_), size(n_), n(n_) {
     for (uint32_t i = 0; i < n_; i++) {
-      pos[i] = (int32_t)i;
+      st[i].pos = (int32_t)i;
+      st[i].prio = 0;
       key_at[i] = i;
     }
     for (int32_t p = 0; p <= kOff; p++) lo[p] = 0;  // nothing has a priority below 0
   }
+  inline void prefetch(uint32_t key) const { __builtin_prefetch(&st[key], 1, 1); }
   inline uint32_t bound(int32_t p) {  // clamped lo[p]
     const size_t i = (size_t)(p + kOff);
     if (i >= lo.size()) lo.resize(std::max(lo.size() * 2, i + 1), n);
@@ -168,33 +173,35 @@ struct GorderQueue {
     const uint32_t ka = key_at[a], kb = key_at[b];
     key_at[a] = kb;
     key_at[b] = ka;
-    pos[kb] = (int32_t)a;
-    pos[ka] = (int32_t)b;
+    st[kb].pos = (int32_t)a;
+    st[ka].pos = (int32_t)b;
   }
   inline bool increment(uint32_t key) {
-    const int32_t s = pos[key];
+    State& k = st[key];
+    const int32_t s = k.pos;
     if (s < 0) return true;
-    const int32_t p = prio[key];
+    const int32_t p = k.prio;
     const uint32_t idx = bound(p + 1) - 1;  // upper_bound - 1: rightmost entry of priority p
-    swap_slots((uint32_t)s, idx);
-    prio[key] = p + 1;
+    k.prio = p + 1;
+    if ((uint32_t)s != idx) swap_slots((uint32_t)s, idx);
     lo[(size_t)(p + 1 + kOff)] = idx;
     return true;
   }
   inline bool decrement(uint32_t key) {
-    const int32_t s = pos[key];
+    State& k = st[key];
+    const int32_t s = k.pos;
     if (s < 0) return true;
-    const int32_t p = prio[key];
+    const int32_t p = k.prio;
     if (p + kOff <= 0) return false;
     const uint32_t idx = bound(p);  // lower_bound: leftmost entry of priority p
-    swap_slots((uint32_t)s, idx);
-    prio[key] = p - 1;
+    k.prio = p - 1;
+    if ((uint32_t)s != idx) swap_slots((uint32_t)s, idx);
     lo[(size_t)(p + kOff)] = idx + 1;
     return true;
   }
   inline uint32_t pop() {
     const uint32_t key = key_at[--size];
-    pos[key] = -1;
+    st[key].pos = -1;
     return key;
   }
 };
@@ -212,19 +219,33 @@ static int gorder_perm(const uint32_t* links, uint32_t n, uint32_t M, int w, std
   order[0] = q.pop();
   for (int64_t i = 1; i < (int64_t)n; i++) {
     const uint32_t ve = order[i - 1];
+    // The order of the queue operations is the reference's; prefetches only warm the per-key state of the keys a few
+    // operations ahead (the sequence is a random walk over ~2200 keys per placed node).
+    constexpr uint64_t kAhead = 8;
+    const uint64_t n_items = out.item.size();
     for (uint64_t e = out.start[ve]; e < out.start[ve + 1]; e++) q.increment(out.item[e]);
     for (uint64_t e = in.start[ve]; e < in.start[ve + 1]; e++) {
       const uint32_t u = in.item[e];
+      if (e + 1 < in.start[ve + 1]) __builtin_prefetch(&out.item[out.start[in.item[e + 1]]], 0, 1);
       q.increment(u);
-      for (uint64_t f = out.start[u]; f < out.start[u + 1]; f++) q.increment(out.item[f]);
+      const uint64_t f1 = out.start[u + 1];
+      for (uint64_t f = out.start[u]; f < f1; f++) {
+        if (f + kAhead < n_items) q.prefetch(out.item[f + kAhead]);
+        q.increment(out.item[f]);
+      }
     }
     if (i > (int64_t)w + 1) {
       const uint32_t vb = order[i - w - 1];
       for (uint64_t e = out.start[vb]; e < out.start[vb + 1]; e++) ok &= q.decrement(out.item[e]);
       for (uint64_t e = in.start[vb]; e < in.start[vb + 1]; e++) {
         const uint32_t u = in.item[e];
+        if (e + 1 < in.start[vb + 1]) __builtin_prefetch(&out.item[out.start[in.item[e + 1]]], 0, 1);
         ok &= q.decrement(u);
-        for (uint64_t f = out.start[u]; f < out.start[u + 1]; f++) ok &= q.decrement(out.item[f]);
+        const uint64_t f1 = out.start[u + 1];
+        for (uint64_t f = out.start[u]; f < f1; f++) {
+          if (f + kAhead < n_items) q.prefetch(out.item[f + kAhead]);
+          ok &= q.decrement(out.item[f]);
+        }
       }
     }
     order[i] = q.pop();
