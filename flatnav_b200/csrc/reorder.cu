@@ -221,7 +221,7 @@ static int gorder_perm(const uint32_t* links, uint32_t n, uint32_t M, int w, std
     const uint32_t ve = order[i - 1];
     // The order of the queue operations is the reference's; prefetches only warm the per-key state of the keys a few
     // operations ahead (the sequence is a random walk over ~2200 keys per placed node).
-    constexpr uint64_t kAhead = 8;
+    constexpr uint64_t kAhead = 12;
     const uint64_t n_items = out.item.size();
     for (uint64_t e = out.start[ve]; e < out.start[ve + 1]; e++) q.increment(out.item[e]);
     for (uint64_t e = in.start[ve]; e < in.start[ve + 1]; e++) {
