@@ -83,7 +83,9 @@ EXPORTS = {
                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "fnb_search_device_totals": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
                                            C.POINTER(C.c_int64)]),
+    "fnb_search_kernel_signature": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_char_p, C.c_size_t]),
     "fnb_bruteforce": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),
+    "fnb_rerank": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "fnb_bruteforce_stats": (C.c_int, [C.POINTER(FnbBfStats)]),
     "fnb_merge_topk": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_void_p, C.c_void_p,
                                  C.c_void_p]),
@@ -110,7 +112,12 @@ def lib() -> C.CDLL:
                 "(or `make -C flatnav_b200/csrc`). flatnav_b200 has no CPU fallback.")
         l = C.CDLL(LIB_PATH)
         for name, (res, args) in EXPORTS.items():
-            fn = getattr(l, name)  # AttributeError if the library does not export a declared symbol
+            try:
+                fn = getattr(l, name)  # AttributeError if the library does not export a declared symbol
+            except AttributeError:
+                if os.environ.get("FNB_LIB_PATH"):  # development A/B against an older build: tolerate newer symbols
+                    continue
+                raise
             fn.restype = res
             fn.argtypes = args
         _lib = l

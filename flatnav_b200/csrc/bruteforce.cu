@@ -140,7 +140,8 @@ extern "C" int fnb_bruteforce(fnb_index* ix, const void* queries, int64_t Q, int
   if (!queries || !out_dist || !out_label) return fail(FNB_ERR_INVALID_ARG, "NULL buffer");
   if (K > 2048) return fail(FNB_ERR_UNSUPPORTED, "brute force supports K <= 2048");
   if (Q >= (1ll << 31)) return fail(FNB_ERR_UNSUPPORTED, "more than 2^31 queries in one call");
-  std::lock_guard<std::mutex> lock(ix->mu);
+  fnb::ExclusiveLock lock(ix->mu);
+  fnb::quiesce(ix);
   Replica& r = ix->replicas[0];
   const Header& h = ix->h;
   int prev = 0;

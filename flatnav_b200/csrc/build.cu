@@ -382,8 +382,8 @@ int fnb_index_create(int metric, int data_type, uint64_t dim, uint64_t max_node_
   return rc;
 }
 
-int fnb_index_reserve(fnb_index* ix, uint64_t max_node_count) {
-  if (!ix) return fail(FNB_ERR_INVALID_ARG, "index is NULL");
+// caller holds the exclusive lock
+static int reserve_locked(fnb_index* ix, uint64_t max_node_count) {
   if (ix->replicas.size() != 1) return fail(FNB_ERR_UNSUPPORTED, "construction works on a single-device index");
   if (max_node_count < ix->h.cur_nodes) return fail(FNB_ERR_INVALID_ARG, "cannot shrink below the current node count");
   if (max_node_count >= (1ull << 31)) return fail(FNB_ERR_UNSUPPORTED, "more than 2^31 nodes");
@@ -425,6 +425,209 @@ int fnb_index_reserve(fnb_index* ix, uint64_t max_node_count) {
   return FNB_OK;
 }
 
+int fnb_index_reserve(fnb_index* ix, uint64_t max_node_count) {
+  if (!ix) return fail(FNB_ERR_INVALID_ARG, "index is NULL");
+  fnb::ExclusiveLock lock(ix->mu);
+  fnb::quiesce(ix);  // an asynchronous search may still be reading the arrays that are about to be replaced
+  return reserve_locked(ix, max_node_count);
+}
+
+}  // extern "C"
+
+// Construction scratch kept on the index between fnb_index_add calls (reference-style loops that add one vector or a
+// small batch at a time must not pay a dozen cudaMalloc / cudaFree and a recount of every node's degree per call).
+struct fnb_build_scratch {
+  uint32_t *deg = nullptr, *ovf_head = nullptr;  // [node_cap]
+  uint64_t node_cap = 0;
+  uint64_t deg_nodes = 0;  // deg[] is current for nodes [0, deg_nodes) — reset by anything else that edits link rows
+  uint32_t *ovf_next = nullptr, *ovf_src = nullptr, *dirty = nullptr;  // [ovf_cap]
+  uint64_t ovf_cap = 0;
+  int32_t* cand_id = nullptr;  // [cand_cap]
+  float* cand_dist = nullptr;
+  uint64_t cand_cap = 0;
+  unsigned int* counters = nullptr;  // 64 B
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+};
+
+void fnb_build_scratch_free(fnb_build_scratch* b) {
+  if (!b) return;
+  cudaFree(b->deg);
+  cudaFree(b->ovf_head);
+  cudaFree(b->ovf_next);
+  cudaFree(b->ovf_src);
+  cudaFree(b->dirty);
+  cudaFree(b->cand_id);
+  cudaFree(b->cand_dist);
+  cudaFree(b->counters);
+  if (b->e0) cudaEventDestroy(b->e0);
+  if (b->e1) cudaEventDestroy(b->e1);
+  delete b;
+}
+
+void fnb_index_mutated(fnb_index* ix, bool links, bool labels) {
+  if (links && ix->build) ix->build->deg_nodes = 0;
+  if (labels && ix->label_map) {
+    fnb_label_map_free(ix->label_map);
+    ix->label_map = nullptr;
+  }
+}
+
+#define S_CU(call)                                                                                            \
+  do {                                                                                                        \
+    cudaError_t e__ = (call);                                                                                 \
+    if (e__ != cudaSuccess)                                                                                   \
+      return fail(FNB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+template <typename T>
+static int grow(T** ptr, uint64_t* cap, uint64_t want, size_t elem, T** twin = nullptr, T** twin2 = nullptr) {
+  if (want <= *cap) return FNB_OK;
+  const uint64_t n = std::max<uint64_t>(want, *cap + *cap / 2);
+  for (T** q : {ptr, twin, twin2}) {
+    if (!q) continue;
+    cudaFree(*q);
+    *q = nullptr;
+  }
+  *cap = 0;
+  for (T** q : {ptr, twin, twin2}) {
+    if (!q) continue;
+    S_CU(cudaMalloc((void**)q, n * elem));
+  }
+  *cap = n;
+  return FNB_OK;
+}
+
+// The body of fnb_index_add; the caller holds the exclusive lock, has validated the arguments and restores the
+// current device.  On a CUDA failure inside the batch loop the index is left with the nodes of the batches that
+// completed (cur_num_nodes says how many): every link still points at a live node.
+static int add_locked(fnb_index* ix, const void* vectors, const int32_t* labels, int64_t n, int ef_construction,
+                      int num_initializations, fnb_build_stats* stats) {
+  Header& h = ix->h;
+  Replica& r = ix->replicas[0];
+  const uint32_t M = (uint32_t)h.M, Msel = std::max(M / 2u, 1u);
+  const uint32_t Kc = (uint32_t)ef_construction;
+  S_CU(cudaSetDevice(r.device));
+  cudaStream_t s = r.stream;
+  if (!ix->build) ix->build = new fnb_build_scratch();
+  fnb_build_scratch& B = *ix->build;
+  if (!B.e0) S_CU(cudaEventCreate(&B.e0));
+  if (!B.e1) S_CU(cudaEventCreate(&B.e1));
+  if (!B.counters) S_CU(cudaMalloc((void**)&B.counters, 64));
+  S_CU(cudaEventRecord(B.e0, s));
+  const uint32_t first = (uint32_t)h.cur_nodes, total = first + (uint32_t)n;
+  const uint32_t max_b = (uint32_t)std::max(1, getenv("FNB_BUILD_BATCH") ? atoi(getenv("FNB_BUILD_BATCH")) : 16384);
+  const uint32_t bmax = (uint32_t)std::min<uint64_t>(max_b, (uint64_t)n);  // no batch of this call is larger
+  const uint32_t ovf_cap = bmax * Msel;
+
+  // ---- upload: vectors (padded rows), labels ----
+  int rc = upload_new_rows_locked(ix, vectors, labels, 0, n, /*init_links=*/false);  // labels NULL: 0 .. n-1 (bindings.cpp:84-86)
+  if (rc != FNB_OK) return rc;
+  // ---- scratch: grown, never shrunk ----
+  {
+    const uint64_t had = B.node_cap;
+    rc = grow(&B.deg, &B.node_cap, r.capacity, 4, &B.ovf_head);
+    if (rc != FNB_OK) return rc;
+    if (B.node_cap != had) B.deg_nodes = 0;
+    rc = grow(&B.ovf_next, &B.ovf_cap, ovf_cap, 4, &B.ovf_src, &B.dirty);
+    if (rc != FNB_OK) return rc;
+    uint64_t cc = B.cand_cap;
+    rc = grow(&B.cand_id, &cc, (uint64_t)bmax * Kc, 4);
+    if (rc != FNB_OK) return rc;
+    rc = grow(&B.cand_dist, &B.cand_cap, (uint64_t)bmax * Kc, 4);
+    if (rc != FNB_OK) return rc;
+  }
+  S_CU(cudaMemsetAsync(B.ovf_head, 0, (size_t)total * 4, s));
+  S_CU(cudaMemsetAsync(B.counters, 0, 64, s));
+  if (B.deg_nodes != first && first) {  // degrees of the existing rows are not known (loaded / re-ordered / imported)
+    build_count_degree_kernel<<<(first + 255) / 256, 256, 0, s>>>(r.adj, B.deg, first, M, B.counters + 8);
+    S_CU(cudaGetLastError());
+    unsigned int unpacked = 0;
+    S_CU(cudaMemcpyAsync(&unpacked, B.counters + 8, 4, cudaMemcpyDeviceToHost, s));
+    S_CU(cudaStreamSynchronize(s));
+    if (unpacked)
+      return fail(FNB_ERR_UNSUPPORTED, "%u nodes have link rows with self-loops before real links; cannot append", unpacked);
+  }
+  B.deg_nodes = 0;  // until this call has finished
+  build_init_rows_kernel<<<(unsigned)(((size_t)n * M + 255) / 256), 256, 0, s>>>(r.adj, B.deg, first, (uint32_t)n, M);
+  S_CU(cudaGetLastError());
+
+  // ---- batched insertion ----
+  SearchParams sp;
+  int64_t n_batches = 0;
+  uint32_t done = first;
+  if (done == 0) done = 1;  // the first node has nothing to link to (Index.h:366-368)
+  auto enqueue_batch = [&](uint32_t b) -> int {
+    // the graph the batch searches is the first `done` nodes; cur_num_nodes itself moves only when a batch is complete
+    int prc = plan_search(ix, b, (int)Kc, (int)Kc, num_initializations, &sp, 0, done);
+    if (prc != FNB_OK) return prc;
+    sp.vec = r.vec;
+    sp.adj = r.adj;
+    sp.labels = nullptr;  // node ids, not labels
+    sp.queries = r.vec + (size_t)done * ix->stride;
+    sp.query_pitch_chunks = ix->stride;
+    sp.out_dist = B.cand_dist;
+    sp.out_label = B.cand_id;
+    sp.counter = r.counter;
+    sp.totals = r.totals;
+    S_CU(cudaMemsetAsync(r.counter, 0, 128, s));
+    S_CU(dispatch_search(ix, sp, r.num_sms, s));
+    BuildParams bp;
+    bp.sp = sp;
+    bp.adj = r.adj;
+    bp.deg = B.deg;
+    bp.cand_id = B.cand_id;
+    bp.cand_dist = B.cand_dist;
+    bp.ovf_head = B.ovf_head;
+    bp.ovf_next = B.ovf_next;
+    bp.ovf_src = B.ovf_src;
+    bp.dirty = B.dirty;
+    bp.counters = B.counters;
+    bp.M = M;
+    bp.Msel = Msel;
+    bp.Kc = Kc;
+    bp.first = done;
+    bp.b = b;
+    bp.ovf_cap = ovf_cap;
+    S_CU(cudaMemsetAsync(B.counters, 0, 8, s));      // overflow entries, dirty nodes
+    S_CU(cudaMemsetAsync(B.counters + 3, 0, 4, s));  // prune work counter
+    S_CU(launch_build_any(ix, bp, r.num_sms, s));
+    return FNB_OK;
+  };
+  while (done < total) {
+    // nodes of one batch cannot link to each other: keep a batch small against the graph it is inserted into
+    // (1/16 while the graph is small and every link matters, 1/8 afterwards)
+    const uint32_t b = std::min({max_b, total - done, std::max(1u, done < 65536u ? done / 16u : done / 8u)});
+    rc = enqueue_batch(b);
+    if (rc != FNB_OK) {
+      // keep what the completed batches built; the rows beyond are uploaded but not part of the graph
+      const std::string keep = g_last_error;
+      if (cudaStreamSynchronize(s) == cudaSuccess) h.cur_nodes = done;
+      g_last_error = keep;
+      return rc;
+    }
+    done += b;
+    n_batches++;
+  }
+  unsigned int hc[4] = {0, 0, 0, 0};
+  S_CU(cudaMemcpyAsync(hc, B.counters, 16, cudaMemcpyDeviceToHost, s));
+  S_CU(cudaEventRecord(B.e1, s));
+  S_CU(cudaStreamSynchronize(s));
+  h.cur_nodes = total;
+  B.deg_nodes = total;
+  fnb_index_mutated(ix, false, true);
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, B.e0, B.e1);
+  if (stats) {
+    stats->n_added = n;
+    stats->n_batches = n_batches;
+    stats->n_dropped_backlinks = hc[2];
+    stats->device_ms = ms;
+  }
+  return FNB_OK;
+}
+
+extern "C" {
+
 int fnb_index_add(fnb_index* ix, const void* vectors, const int32_t* labels, int64_t n, int ef_construction,
                   int num_initializations, fnb_build_stats* stats) {
   if (!ix) return fail(FNB_ERR_INVALID_ARG, "index is NULL");
@@ -435,141 +638,22 @@ int fnb_index_add(fnb_index* ix, const void* vectors, const int32_t* labels, int
   if (n == 0) return FNB_OK;
   if (!vectors) return fail(FNB_ERR_INVALID_ARG, "vectors is NULL");
   if (ix->replicas.size() != 1) return fail(FNB_ERR_UNSUPPORTED, "construction works on a single-device index");
-  std::lock_guard<std::mutex> lock(ix->mu);
+  fnb::ExclusiveLock lock(ix->mu);
+  fnb::quiesce(ix);
   Header& h = ix->h;
   Replica& r = ix->replicas[0];
-  if (h.cur_nodes + (uint64_t)n > h.max_nodes || h.cur_nodes + (uint64_t)n > r.capacity)
+  if (h.cur_nodes + (uint64_t)n > h.max_nodes)
     return fail(FNB_ERR_INVALID_ARG, "Maximum number of nodes reached. Consider increasing the `max_node_count` parameter to "
                                      "create a larger index.");  // Index.h:356-361
-  const uint32_t M = (uint32_t)h.M, Msel = std::max(M / 2u, 1u);
-  if (M > BUILD_TMAX / 2) return fail(FNB_ERR_UNSUPPORTED, "construction supports max_edges_per_node <= %d", BUILD_TMAX / 2);
-  const uint32_t Kc = (uint32_t)ef_construction;
+  if ((uint32_t)h.M > BUILD_TMAX / 2) return fail(FNB_ERR_UNSUPPORTED, "construction supports max_edges_per_node <= %d", BUILD_TMAX / 2);
   int prev = 0;
   cudaGetDevice(&prev);
-  std::vector<void*> tmp;
-  B_CU(cudaSetDevice(r.device));
-  cudaStream_t s = r.stream;
-  cudaEvent_t e0, e1;
-  B_CU(cudaEventCreate(&e0));
-  B_CU(cudaEventCreate(&e1));
-  B_CU(cudaEventRecord(e0, s));
-  const uint32_t first = (uint32_t)h.cur_nodes, total = first + (uint32_t)n;
-  const size_t rowb = (size_t)ix->stride * FNB_CHUNK_BYTES;
-  const uint32_t max_b = (uint32_t)std::max(1, getenv("FNB_BUILD_BATCH") ? atoi(getenv("FNB_BUILD_BATCH")) : 16384);
-  const uint32_t ovf_cap = max_b * Msel;
-
-  // ---- upload: vectors (padded rows), labels ----
-  {
-    const int rc = upload_new_rows_locked(ix, vectors, labels, 0, n, /*init_links=*/false);  // labels NULL: 0 .. n-1 (bindings.cpp:84-86)
-    if (rc != FNB_OK) {
-      cudaEventDestroy(e0);
-      cudaEventDestroy(e1);
-      cudaSetDevice(prev);
-      return rc;
-    }
-  }
-  uint32_t *deg = nullptr, *ovf_head = nullptr, *ovf_next = nullptr, *ovf_src = nullptr, *dirty = nullptr;
-  unsigned int* counters = nullptr;
-  int32_t* cand_id = nullptr;
-  float* cand_dist = nullptr;
-#define B_ALLOC(ptr, bytes)                 \
-  B_CU(cudaMalloc((void**)&ptr, (bytes)));  \
-  tmp.push_back(ptr)
-  B_ALLOC(deg, (size_t)total * 4);
-  B_ALLOC(ovf_head, (size_t)total * 4);
-  B_ALLOC(ovf_next, (size_t)ovf_cap * 4);
-  B_ALLOC(ovf_src, (size_t)ovf_cap * 4);
-  B_ALLOC(dirty, (size_t)ovf_cap * 4);
-  B_ALLOC(counters, 64);
-  B_ALLOC(cand_id, (size_t)max_b * Kc * 4);
-  B_ALLOC(cand_dist, (size_t)max_b * Kc * 4);
-  B_CU(cudaMemsetAsync(ovf_head, 0, (size_t)total * 4, s));
-  B_CU(cudaMemsetAsync(counters, 0, 64, s));
-  if (first) {
-    build_count_degree_kernel<<<(first + 255) / 256, 256, 0, s>>>(r.adj, deg, first, M, counters + 8);
-    B_CU(cudaGetLastError());
-    unsigned int unpacked = 0;
-    B_CU(cudaMemcpyAsync(&unpacked, counters + 8, 4, cudaMemcpyDeviceToHost, s));
-    B_CU(cudaStreamSynchronize(s));
-    if (unpacked) {
-      for (void* ptr : tmp) cudaFree(ptr);
-      cudaSetDevice(prev);
-      return fail(FNB_ERR_UNSUPPORTED, "%u nodes have link rows with self-loops before real links; cannot append", unpacked);
-    }
-  }
-  build_init_rows_kernel<<<(unsigned)(((size_t)n * M + 255) / 256), 256, 0, s>>>(r.adj, deg, first, (uint32_t)n, M);
-  B_CU(cudaGetLastError());
-
-  // ---- batched insertion ----
-  SearchParams sp;
-  int64_t n_batches = 0;
-  uint32_t done = first;
-  if (done == 0) done = 1;  // the first node has nothing to link to (Index.h:366-368)
-  while (done < total) {
-    // nodes of one batch cannot link to each other: keep a batch small against the graph it is inserted into
-    // (1/16 while the graph is small and every link matters, 1/8 afterwards)
-    const uint32_t b = std::min({max_b, total - done, std::max(1u, done < 65536u ? done / 16u : done / 8u)});
-    h.cur_nodes = done;  // the graph the batch searches
-    int rc = plan_search(ix, b, (int)Kc, (int)Kc, num_initializations, &sp);
-    if (rc != FNB_OK) {
-      h.cur_nodes = first;
-      for (void* ptr : tmp) cudaFree(ptr);
-      cudaSetDevice(prev);
-      return rc;
-    }
-    sp.vec = r.vec;
-    sp.adj = r.adj;
-    sp.labels = nullptr;  // node ids, not labels
-    sp.queries = r.vec + (size_t)done * ix->stride;
-    sp.query_pitch_chunks = ix->stride;
-    sp.out_dist = cand_dist;
-    sp.out_label = cand_id;
-    sp.counter = r.counter;
-    sp.totals = r.totals;
-    B_CU(cudaMemsetAsync(r.counter, 0, 4, s));
-    B_CU(cudaMemsetAsync(r.totals, 0, 24, s));
-    B_CU(dispatch_search(ix, sp, r.num_sms, s));
-    BuildParams bp;
-    bp.sp = sp;
-    bp.adj = r.adj;
-    bp.deg = deg;
-    bp.cand_id = cand_id;
-    bp.cand_dist = cand_dist;
-    bp.ovf_head = ovf_head;
-    bp.ovf_next = ovf_next;
-    bp.ovf_src = ovf_src;
-    bp.dirty = dirty;
-    bp.counters = counters;
-    bp.M = M;
-    bp.Msel = Msel;
-    bp.Kc = Kc;
-    bp.first = done;
-    bp.b = b;
-    bp.ovf_cap = ovf_cap;
-    B_CU(cudaMemsetAsync(counters, 0, 8, s));        // overflow entries, dirty nodes
-    B_CU(cudaMemsetAsync(counters + 3, 0, 4, s));    // prune work counter
-    B_CU(launch_build_any(ix, bp, r.num_sms, s));
-    done += b;
-    n_batches++;
-  }
-  h.cur_nodes = total;
-  unsigned int hc[4] = {0, 0, 0, 0};
-  B_CU(cudaMemcpyAsync(hc, counters, 16, cudaMemcpyDeviceToHost, s));
-  B_CU(cudaEventRecord(e1, s));
-  B_CU(cudaStreamSynchronize(s));
-  float ms = 0.f;
-  cudaEventElapsedTime(&ms, e0, e1);
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
-  for (void* ptr : tmp) cudaFree(ptr);
+  int rc = FNB_OK;
+  // a loaded index holds exactly cur_num_nodes rows although its header allows max_node_count: make room
+  if (h.cur_nodes + (uint64_t)n > r.capacity) rc = reserve_locked(ix, h.max_nodes);
+  if (rc == FNB_OK) rc = add_locked(ix, vectors, labels, n, ef_construction, num_initializations, stats);
   cudaSetDevice(prev);
-  if (stats) {
-    stats->n_added = n;
-    stats->n_batches = n_batches;
-    stats->n_dropped_backlinks = hc[2];
-    stats->device_ms = ms;
-  }
-  return FNB_OK;
+  return rc;
 }
 
 }  // extern "C"

@@ -90,18 +90,23 @@ __global__ void __launch_bounds__(256) exchange_merge_kernel(const ExchangeParam
     __threadfence_system();
     st_release_sys(p.flags[threadIdx.x] + p.rank, p.epoch);
   }
+  __shared__ unsigned int s_timeout;
+  if (threadIdx.x == 0) s_timeout = 0u;
+  __syncthreads();
   if (threadIdx.x < p.world && threadIdx.x != p.rank) {
     const uint32_t* f = p.flags[p.rank] + threadIdx.x;
     const unsigned long long t0 = globaltimer_ns();
     while ((int32_t)(ld_acquire_sys(f) - p.epoch) < 0) {
       if (globaltimer_ns() - t0 > 20000000000ull) {  // 20 s: a peer died; report instead of hanging the GPU
         atomicExch(p.ctl + 1, 1u);
+        s_timeout = 1u;
         break;
       }
       __nanosleep(200);
     }
   }
   __syncthreads();
+  const bool stale = s_timeout != 0u;  // some peer's lists never arrived: do not merge what an older epoch left there
   // ---- 3. k-way merge of the `world` sorted lists of each query (one warp per query, ties -> lower label) ----
   const int lane = threadIdx.x & 31;
   const size_t warps = nthreads >> 5;
@@ -125,8 +130,9 @@ __global__ void __launch_bounds__(256) exchange_merge_kernel(const ExchangeParam
         best = o < best ? o : best;
       }
       if (lane == 0) {
-        p.out_dist[qi * p.K + j] = best == ~0ull ? __int_as_float(0x7f800000) : unord_f32((uint32_t)(best >> 32));
-        p.out_label[qi * p.K + j] = best == ~0ull ? -1 : (int32_t)(uint32_t)best;
+        const bool none = stale || best == ~0ull;
+        p.out_dist[qi * p.K + j] = none ? __int_as_float(0x7f800000) : unord_f32((uint32_t)(best >> 32));
+        p.out_label[qi * p.K + j] = none ? -1 : (int32_t)(uint32_t)best;
       }
       if (best != ~0ull && cur == best) {
         head++;
@@ -242,7 +248,10 @@ int fnb_search_sharded(fnb_index* ix, fnb_exchange* ex, const void* d_queries, i
   if (!d_out_dist || !d_out_label) return fail(FNB_ERR_INVALID_ARG, "NULL buffer");
   if (ix->replicas[0].device != ex->device) return fail(FNB_ERR_INVALID_ARG, "index and exchange live on different devices");
   cudaStream_t s = (cudaStream_t)cuda_stream;
-  const uint32_t epoch = ++ex->epoch;
+  // The epoch is committed only when both kernels of this call are enqueued: a call that fails before that (bad
+  // arguments, a plan that does not fit, a launch error) must not leave this rank one epoch ahead of peers it never
+  // signalled.
+  const uint32_t epoch = ex->epoch + 1u;
   const size_t half = (epoch & 1u) * ex->half_elems;
   const size_t n = (size_t)Q * K;
   ExchangeParams p;
@@ -278,6 +287,7 @@ int fnb_search_sharded(fnb_index* ix, fnb_exchange* ex, const void* d_queries, i
   cudaError_t e = cudaGetLastError();
   cudaSetDevice(prev);
   if (e != cudaSuccess) return fail(FNB_ERR_CUDA, "exchange kernel launch failed: %s", cudaGetErrorString(e));
+  ex->epoch = epoch;
   return FNB_OK;
 }
 
@@ -290,7 +300,17 @@ int fnb_exchange_status(fnb_exchange* ex) {
   cudaError_t e = cudaMemcpy(ctl, ex->ctl, 8, cudaMemcpyDeviceToHost);
   cudaSetDevice(prev);
   if (e != cudaSuccess) return fail(FNB_ERR_CUDA, "cudaMemcpy failed: %s", cudaGetErrorString(e));
-  if (ctl[1]) return fail(FNB_ERR_CUDA, "a peer rank did not deliver its results within 20 s");
+  if (ctl[1]) {
+    // the flag is consumed by this read; the affected calls returned +inf / -1 everywhere.  The ranks' epochs may have
+    // diverged (the peer that failed did not advance): re-create the exchange before searching again.
+    int prev2 = 0;
+    cudaGetDevice(&prev2);
+    cudaSetDevice(ex->device);
+    cudaMemset(ex->ctl + 1, 0, 4);
+    cudaSetDevice(prev2);
+    return fail(FNB_ERR_CUDA, "a peer rank did not deliver its results within 20 s; the outputs of that search are "
+                              "+inf / -1 and the exchange must be re-created");
+  }
   return FNB_OK;
 }
 

@@ -114,6 +114,13 @@ static int parse_header(const unsigned char* p, size_t nbytes, int metric, int e
   if (es == 0) return fail(FNB_ERR_FORMAT, "unsupported data_type %d in index header", dt);
   if (expect_dtype != FNB_DTYPE_ANY && expect_dtype != dt)
     return fail(FNB_ERR_FORMAT, "index holds data_type %d but %d was requested", dt, expect_dtype);
+  // bound every field BEFORE multiplying: a crafted header must not wrap the size arithmetic below (or the kernels'
+  // 32-bit copies of M / dim)
+  if (h->M == 0 || h->dim == 0) return fail(FNB_ERR_FORMAT, "M and dim must be positive");
+  if (h->M > 65536) return fail(FNB_ERR_UNSUPPORTED, "max_edges_per_node %llu exceeds 65536", (unsigned long long)h->M);
+  if (h->dim > (uint64_t)FNB_MAX_CHUNKS * FNB_CHUNK_BYTES)
+    return fail(FNB_ERR_UNSUPPORTED, "dimension %llu exceeds what the kernels are built for", (unsigned long long)h->dim);
+  if (h->max_nodes >= (1ull << 31)) return fail(FNB_ERR_UNSUPPORTED, "more than 2^31 nodes");
   if (v[6] != h->data_size || h->dim * es != h->data_size)
     return fail(FNB_ERR_FORMAT, "header inconsistent: dim=%llu data_size=%llu/%llu", (unsigned long long)h->dim,
                 (unsigned long long)h->data_size, (unsigned long long)v[6]);
@@ -121,8 +128,7 @@ static int parse_header(const unsigned char* p, size_t nbytes, int metric, int e
     return fail(FNB_ERR_FORMAT, "header inconsistent: node_size %llu != data_size + 4M + 4",
                 (unsigned long long)h->node_size);
   if (h->cur_nodes > h->max_nodes) return fail(FNB_ERR_FORMAT, "cur_num_nodes > max_node_count");
-  if (h->M == 0 || h->dim == 0) return fail(FNB_ERR_FORMAT, "M and dim must be positive");
-  if (h->max_nodes >= (1ull << 31)) return fail(FNB_ERR_UNSUPPORTED, "more than 2^31 nodes");
+  // node_size <= 8 KB + 256 KB + 4 and max_nodes < 2^31: the product fits 64 bits
   if (nbytes < FNB_HEADER_BYTES + h->node_size * h->max_nodes)
     return fail(FNB_ERR_FORMAT, "index file truncated: %zu bytes, need %llu", nbytes,
                 (unsigned long long)(FNB_HEADER_BYTES + h->node_size * h->max_nodes));
@@ -159,50 +165,148 @@ static int upload_replica(const Header& h, const unsigned char* blob, int device
   CU(cudaMalloc(&r->vec, n * stride * FNB_CHUNK_BYTES));
   CU(cudaMalloc(&r->adj, n * h.M * 4));
   CU(cudaMalloc(&r->labels, n * 4));
-  CU(cudaMalloc(&r->counter, 64));
-  CU(cudaMalloc(&r->totals, 64));
-  CU(cudaMallocHost(&r->h_totals, 64));
+  CU(cudaMalloc(&r->counter, 128));
+  r->totals = reinterpret_cast<unsigned long long*>(r->counter + 16);
   CU(cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking));
-  CU(cudaEventCreate(&r->ev[0]));
-  CU(cudaEventCreate(&r->ev[1]));
-  CU(cudaEventCreate(&r->ev[2]));
-  CU(cudaEventCreate(&r->ev[3]));
+  r->pool = new LanePool();
+  if (const char* e = getenv("FNB_MAX_LANES")) r->pool->max_lanes = std::max(1, atoi(e));
+  CU(cudaMalloc(&r->pool->ring, FNB_RING_SLOTS * 64));
   r->device_bytes = n * stride * FNB_CHUNK_BYTES + n * h.M * 4 + n * 4;
   r->capacity = n;
   if (h.cur_nodes) {
     CU(cudaMalloc(&d_blob, blob_bytes));
-    CU(cudaMemcpy(d_blob, blob, blob_bytes, cudaMemcpyHostToDevice));
+    CU(cudaMemcpyAsync(d_blob, blob, blob_bytes, cudaMemcpyHostToDevice, r->stream));
     const int threads = 256;
     const int blocks = (int)std::min<uint64_t>((h.cur_nodes * 32 + threads - 1) / threads, (uint64_t)r->num_sms * 32);
-    deinterleave_kernel<<<blocks, threads>>>(d_blob, h.cur_nodes, h.node_size, (uint32_t)h.data_size, (uint32_t)h.M,
+    deinterleave_kernel<<<blocks, threads, 0, r->stream>>>(d_blob, h.cur_nodes, h.node_size, (uint32_t)h.data_size, (uint32_t)h.M,
                                              stride * FNB_CHUNK_BYTES, reinterpret_cast<unsigned char*>(r->vec),
                                              r->adj, r->labels);
     CU(cudaGetLastError());
-    CU(cudaMemset(r->counter, 0, 64));
-    validate_links_kernel<<<r->num_sms * 8, 256>>>(r->adj, h.cur_nodes * h.M, (uint32_t)h.cur_nodes, r->counter);
+    CU(cudaMemsetAsync(r->counter, 0, 64, r->stream));
+    validate_links_kernel<<<r->num_sms * 8, 256, 0, r->stream>>>(r->adj, h.cur_nodes * h.M, (uint32_t)h.cur_nodes, r->counter);
     CU(cudaGetLastError());
     unsigned int bad = 0;
-    CU(cudaMemcpy(&bad, r->counter, 4, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpyAsync(&bad, r->counter, 4, cudaMemcpyDeviceToHost, r->stream));
+    CU(cudaStreamSynchronize(r->stream));
     CU(cudaFree(d_blob));
     if (bad) return fail(FNB_ERR_FORMAT, "%u links point outside [0, cur_num_nodes)", bad);
   }
   return FNB_OK;
 }
 
+static void free_lane(Lane* l) {
+  if (!l) return;
+  cudaFree(l->counter);
+  if (l->h_totals) cudaFreeHost(l->h_totals);
+  cudaFree(l->ws);
+  if (l->h_pinned) cudaFreeHost(l->h_pinned);
+  if (l->stream) cudaStreamDestroy(l->stream);
+  if (l->copy_stream) cudaStreamDestroy(l->copy_stream);
+  for (auto& e : l->ev)
+    if (e) cudaEventDestroy(e);
+  if (l->ev_feed) cudaEventDestroy(l->ev_feed);
+  delete l;
+}
+
 static void free_replica(Replica* r) {
   if (r->device < 0) return;
   cudaSetDevice(r->device);
+  cudaDeviceSynchronize();
   cudaFree(r->vec);
   cudaFree(r->adj);
   cudaFree(r->labels);
   cudaFree(r->counter);
-  cudaFree(r->totals);
-  if (r->h_totals) cudaFreeHost(r->h_totals);
-  cudaFree(r->ws);
-  if (r->h_pinned) cudaFreeHost(r->h_pinned);
   if (r->stream) cudaStreamDestroy(r->stream);
-  for (auto& e : r->ev)
-    if (e) cudaEventDestroy(e);
+  if (r->pool) {
+    for (Lane* l : r->pool->all) free_lane(l);
+    cudaFree(r->pool->ring);
+    delete r->pool;
+    r->pool = nullptr;
+  }
+}
+
+// ---- search lanes ------------------------------------------------------------------------------------
+// The calling thread's current device must be r.device.
+static int new_lane(Lane** out) {
+  Lane* l = new Lane();
+  cudaError_t e = cudaStreamCreateWithFlags(&l->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaMalloc(&l->counter, 128);
+  if (e == cudaSuccess) e = cudaMemset(l->counter, 0, 128);
+  if (e == cudaSuccess) e = cudaMallocHost(&l->h_totals, 64 + (FNB_FEED_CHUNKS + 1) * 4);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&l->copy_stream, cudaStreamNonBlocking);
+  for (int i = 0; i < 4 && e == cudaSuccess; i++) e = cudaEventCreate(&l->ev[i]);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&l->ev_feed, cudaEventDisableTiming);
+  if (e != cudaSuccess) {
+    free_lane(l);
+    return fail(FNB_ERR_CUDA, "cannot create a search lane: %s", cudaGetErrorString(e));
+  }
+  l->totals = reinterpret_cast<unsigned long long*>(l->counter + 16);
+  l->q_ready = l->counter + 8;
+  l->h_marks = reinterpret_cast<uint32_t*>(l->h_totals + 8);
+  l->h_marks[FNB_FEED_CHUNKS] = 0xffffffffu;  // "everything is there": releases a launch whose feeding was cut short
+  *out = l;
+  return FNB_OK;
+}
+
+static int acquire_lane(Replica& r, Lane** out) {
+  LanePool& P = *r.pool;
+  std::unique_lock<std::mutex> lk(P.mu);
+  for (;;) {
+    if (!P.idle.empty()) {
+      *out = P.idle.back();
+      P.idle.pop_back();
+      return FNB_OK;
+    }
+    if ((int)P.all.size() < P.max_lanes) {
+      Lane* l = nullptr;
+      const int rc = new_lane(&l);
+      if (rc != FNB_OK) return rc;
+      P.all.push_back(l);
+      *out = l;
+      return FNB_OK;
+    }
+    P.cv.wait(lk);
+  }
+}
+
+static void release_lane(Replica& r, Lane* l) {
+  LanePool& P = *r.pool;
+  {
+    std::lock_guard<std::mutex> lk(P.mu);
+    P.idle.push_back(l);
+  }
+  P.cv.notify_one();
+}
+
+// A lane held for the length of one fnb_search call.  Whatever way the call ends, nothing it enqueued may still be
+// running into the caller's buffers when it returns: the destructor waits for the stream before handing the lane back.
+struct LaneHold {
+  Replica* r = nullptr;
+  Lane* l = nullptr;
+  bool feeding = false;  // a host-fed launch has not been fed to the end yet
+  LaneHold() = default;
+  LaneHold(const LaneHold&) = delete;
+  LaneHold& operator=(const LaneHold&) = delete;
+  LaneHold(LaneHold&& o) noexcept : r(o.r), l(o.l), feeding(o.feeding) { o.l = nullptr; }
+  ~LaneHold() {
+    if (!l) return;
+    cudaSetDevice(r->device);
+    // leaving early (an error after the launch): let the waiting warps through, the call fails anyway
+    if (feeding) cudaMemcpyAsync(l->q_ready, l->h_marks + FNB_FEED_CHUNKS, 4, cudaMemcpyHostToDevice, l->copy_stream);
+    cudaStreamSynchronize(l->stream);
+    release_lane(*r, l);
+  }
+};
+
+void quiesce(fnb_index* ix) {
+  int prev = 0;
+  cudaGetDevice(&prev);
+  for (Replica& r : ix->replicas) {
+    if (r.device < 0) continue;
+    cudaSetDevice(r.device);
+    cudaDeviceSynchronize();
+  }
+  cudaSetDevice(prev);
 }
 
 static int build_index(const unsigned char* file, size_t nbytes, int metric, int expect_dtype, const int* device_ids,
@@ -254,14 +358,16 @@ static int build_index(const unsigned char* file, size_t nbytes, int metric, int
 
 // ---- search dispatch ---------------------------------------------------------------------------------
 // launch_q: queries per kernel launch (the occupancy plan depends on it); <= 0 means Q
-int plan_search(const fnb_index* ix, int64_t Q, int K, int ef, int ninit, SearchParams* p, int64_t launch_q) {
+int plan_search(const fnb_index* ix, int64_t Q, int K, int ef, int ninit, SearchParams* p, int64_t launch_q,
+                uint64_t n_nodes) {
   if (Q < 0) return fail(FNB_ERR_INVALID_ARG, "negative query count");
   if (K <= 0) return fail(FNB_ERR_INVALID_ARG, "K must be positive");
   if (ninit <= 0) return fail(FNB_ERR_INVALID_ARG, "num_initializations must be greater than 0.");
   if (Q >= (1ll << 31)) return fail(FNB_ERR_UNSUPPORTED, "more than 2^31 queries in one call");
   const Header& h = ix->h;
+  const uint64_t cur_nodes = n_nodes ? n_nodes : h.cur_nodes;
   memset(p, 0, sizeof(*p));
-  p->N = (uint32_t)h.cur_nodes;
+  p->N = (uint32_t)cur_nodes;
   p->M = (uint32_t)h.M;
   p->dim = (uint32_t)h.dim;
   p->nchunks = ix->nchunks;
@@ -271,7 +377,7 @@ int plan_search(const fnb_index* ix, int64_t Q, int K, int ef, int ninit, Search
   p->B = (uint32_t)std::max(ef, K);  // Index.h:392
   p->Bcap = (p->B + 31u) & ~31u;
   // Index.h:851-852: step = cur_num_nodes / num_initializations (integer), at least 1
-  uint32_t step = (uint32_t)(h.cur_nodes / (uint64_t)ninit);
+  uint32_t step = (uint32_t)(cur_nodes / (uint64_t)ninit);
   p->step = step ? step : 1;
   p->nprobe = p->N ? (p->N + p->step - 1) / p->step : 0;
   p->query_vec_ok = (h.data_size % FNB_CHUNK_BYTES) == 0 ? 1u : 0u;
@@ -299,7 +405,7 @@ cudaError_t dispatch_search(const fnb_index* ix, const SearchParams& p, int num_
   }
 }
 
-static int ensure_workspace(Replica* r, size_t dev_bytes, size_t host_bytes) {
+static int ensure_workspace(Lane* r, size_t dev_bytes, size_t host_bytes) {
   if (dev_bytes > r->ws_bytes) {
     if (r->ws) CU(cudaFree(r->ws));
     r->ws = nullptr;
@@ -366,6 +472,9 @@ void fnb_index_free(fnb_index* ix) {
   if (!ix) return;
   int prev = 0;
   cudaGetDevice(&prev);
+  if (!ix->replicas.empty() && ix->replicas[0].device >= 0) cudaSetDevice(ix->replicas[0].device);
+  fnb_build_scratch_free(ix->build);
+  fnb_label_map_free(ix->label_map);
   for (auto& r : ix->replicas) free_replica(&r);
   cudaSetDevice(prev);
   delete ix;
@@ -390,12 +499,31 @@ int fnb_index_info(const fnb_index* ix, fnb_info* out) {
   return FNB_OK;
 }
 
+// scoped device buffer / device selection for the entry points below
+namespace {
+struct DevBuf {
+  void* p = nullptr;
+  ~DevBuf() { cudaFree(p); }
+};
+struct DeviceScope {
+  int prev = 0;
+  DeviceScope() { cudaGetDevice(&prev); }
+  ~DeviceScope() { cudaSetDevice(prev); }
+};
+struct LastDeviceCall {  // which ring slot the calling thread's last fnb_search_device used
+  const fnb_index* ix = nullptr;
+  int replica = -1;
+  uint32_t slot = 0;
+};
+thread_local LastDeviceCall t_last_device_call;
+}  // namespace
+
 int fnb_index_save(const fnb_index* ix, const char* path) {
   if (!ix || !path) return fail(FNB_ERR_INVALID_ARG, "NULL argument");
+  SharedLock lock(ix->mu);
   const Header& h = ix->h;
   const Replica& r = ix->replicas[0];
-  int prev = 0;
-  cudaGetDevice(&prev);
+  DeviceScope scope;
   CU(cudaSetDevice(r.device));
   const uint64_t blob_bytes = h.node_size * h.max_nodes;
   std::vector<unsigned char> host(FNB_HEADER_BYTES + blob_bytes, 0);
@@ -404,18 +532,23 @@ int fnb_index_save(const fnb_index* ix, const char* path) {
   memcpy(host.data(), &dt, 4);
   memcpy(host.data() + 4, v, 56);
   if (h.cur_nodes) {
-    unsigned char* d_blob = nullptr;
-    CU(cudaMalloc(&d_blob, h.node_size * h.cur_nodes));
+    DevBuf blob;
+    cudaStream_t s = nullptr;
+    CU(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    struct StreamGuard {
+      cudaStream_t s;
+      ~StreamGuard() { cudaStreamDestroy(s); }
+    } sg{s};
+    CU(cudaMalloc(&blob.p, h.node_size * h.cur_nodes));
     const int threads = 256;
     const int blocks = (int)std::min<uint64_t>((h.cur_nodes * 32 + threads - 1) / threads, (uint64_t)r.num_sms * 32);
-    interleave_kernel<<<blocks, threads>>>(d_blob, h.cur_nodes, h.node_size, (uint32_t)h.data_size, (uint32_t)h.M,
-                                           ix->stride * FNB_CHUNK_BYTES, reinterpret_cast<const unsigned char*>(r.vec),
-                                           r.adj, r.labels);
+    interleave_kernel<<<blocks, threads, 0, s>>>(static_cast<unsigned char*>(blob.p), h.cur_nodes, h.node_size,
+                                                 (uint32_t)h.data_size, (uint32_t)h.M, ix->stride * FNB_CHUNK_BYTES,
+                                                 reinterpret_cast<const unsigned char*>(r.vec), r.adj, r.labels);
     CU(cudaGetLastError());
-    CU(cudaMemcpy(host.data() + FNB_HEADER_BYTES, d_blob, h.node_size * h.cur_nodes, cudaMemcpyDeviceToHost));
-    CU(cudaFree(d_blob));
+    CU(cudaMemcpyAsync(host.data() + FNB_HEADER_BYTES, blob.p, h.node_size * h.cur_nodes, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
   }
-  cudaSetDevice(prev);
   FILE* f = fopen(path, "wb");
   if (!f) return fail(FNB_ERR_IO, "Unable to open file for writing: %s", path);
   size_t put = fwrite(host.data(), 1, host.size(), f);
@@ -429,6 +562,7 @@ int fnb_search_device(fnb_index* ix, int replica, const void* d_queries, int64_t
                       uint32_t* d_nhops, void* cuda_stream) {
   if (!ix) return fail(FNB_ERR_INVALID_ARG, "index is NULL");
   if (replica < 0 || replica >= (int)ix->replicas.size()) return fail(FNB_ERR_INVALID_ARG, "bad replica %d", replica);
+  SharedLock lock(ix->mu);  // the plan reads cur_num_nodes: not while a construction batch is changing it
   SearchParams p;
   int rc = plan_search(ix, Q, K, ef_search, num_initializations, &p);
   if (rc != FNB_OK) return rc;
@@ -436,9 +570,11 @@ int fnb_search_device(fnb_index* ix, int replica, const void* d_queries, int64_t
   if (!d_queries || !d_out_dist || !d_out_label) return fail(FNB_ERR_INVALID_ARG, "NULL buffer");
   Replica& r = ix->replicas[replica];
   cudaStream_t s = (cudaStream_t)cuda_stream;
-  int prev = 0;
-  cudaGetDevice(&prev);
+  DeviceScope scope;
   CU(cudaSetDevice(r.device));
+  // every call gets its own {counter, totals} slot, so calls on different streams may overlap
+  const uint32_t slot = r.pool->ring_seq.fetch_add(1u) % FNB_RING_SLOTS;
+  unsigned char* sl = r.pool->ring + (size_t)slot * 64;
   p.vec = r.vec;
   p.adj = r.adj;
   p.labels = r.labels;
@@ -448,36 +584,70 @@ int fnb_search_device(fnb_index* ix, int replica, const void* d_queries, int64_t
   p.out_label = d_out_label;
   p.out_ndist = d_ndist;
   p.out_nhops = d_nhops;
-  p.counter = r.counter;
-  p.totals = r.totals;
+  p.counter = reinterpret_cast<unsigned int*>(sl);
+  p.totals = reinterpret_cast<unsigned long long*>(sl + 16);
   p.lat = choose_latency_variant(Q, r.num_sms);
-  if (!p.lat) CU(cudaMemsetAsync(r.counter, 0, 4, s));
-  CU(cudaMemsetAsync(r.totals, 0, 24, s));
+  CU(cudaMemsetAsync(sl, 0, 64, s));
   cudaError_t e = dispatch_search(ix, p, r.num_sms, s);
-  cudaSetDevice(prev);
   if (e != cudaSuccess) return fail(FNB_ERR_CUDA, "search kernel launch failed: %s", cudaGetErrorString(e));
+  t_last_device_call.ix = ix;
+  t_last_device_call.replica = replica;
+  t_last_device_call.slot = slot;
   return FNB_OK;
 }
 
-// Reads the totals written by the last fnb_search_device call on `replica` (after the caller synchronised).
+// Name of the traversal-kernel instantiation a search of this shape launches, spelled as ncu prints it.
+int fnb_search_kernel_signature(const fnb_index* ix, int64_t Q, int K, int ef_search, char* out, size_t cap) {
+  if (!ix || !out || cap == 0) return fail(FNB_ERR_INVALID_ARG, "NULL argument");
+  SearchParams p;
+  int rc = plan_search(ix, Q, K, ef_search, 100, &p);
+  if (rc != FNB_OK) return rc;
+  const int sms = ix->replicas.empty() ? 148 : ix->replicas[0].num_sms;
+  const int lat = (int)choose_latency_variant(Q, sms);
+  const int ch = fnb_chunks_per_lane(ix->nchunks, ix->G);
+  int CH;
+  if (ix->G == 4) CH = ch <= 1 ? 1 : 2;
+  else if (ix->G == 8) CH = ch <= 3 ? ch : 4;
+  else CH = ch <= 2 ? 2 : (ch <= 4 ? 4 : (ch <= 8 ? 8 : 16));
+  const int dt = ix->h.data_type == FNB_DTYPE_FLOAT32 ? DT_F32 : (ix->h.data_type == FNB_DTYPE_UINT8 ? DT_U8 : DT_I8);
+  const int exact = p.nchunks == (uint32_t)(ix->G * CH) ? 1 : 0;
+  const int occ = (!lat && p.dense && CH <= 4 && ix->G <= 8) ? FNB_CTAS_DENSE : 0;
+  snprintf(out, cap, "fnb_search_kernel<%d,%d,%d,%d,%d,%d,%d>", dt, ix->h.metric == FNB_METRIC_IP ? M_IP : M_L2, ix->G, CH,
+           exact, lat, occ);
+  return FNB_OK;
+}
+
+// Reads the totals written by the calling thread's last fnb_search_device call on `replica` (after the caller
+// synchronised the stream it used).
 int fnb_search_device_totals(fnb_index* ix, int replica, int64_t* n_dist, int64_t* n_hops, int64_t* n_short) {
   if (!ix || replica < 0 || replica >= (int)ix->replicas.size()) return fail(FNB_ERR_INVALID_ARG, "bad argument");
+  if (t_last_device_call.ix != ix || t_last_device_call.replica != replica)
+    return fail(FNB_ERR_INVALID_ARG, "this thread has not called fnb_search_device on replica %d of this index", replica);
   Replica& r = ix->replicas[replica];
-  int prev = 0;
-  cudaGetDevice(&prev);
+  DeviceScope scope;
   CU(cudaSetDevice(r.device));
   unsigned long long t[3];
-  CU(cudaMemcpy(t, r.totals, sizeof(t), cudaMemcpyDeviceToHost));
-  cudaSetDevice(prev);
+  CU(cudaMemcpy(t, r.pool->ring + (size_t)t_last_device_call.slot * 64 + 16, sizeof(t), cudaMemcpyDeviceToHost));
   if (n_dist) *n_dist = (int64_t)t[0];
   if (n_hops) *n_hops = (int64_t)t[1];
   if (n_short) *n_short = (int64_t)t[2];
   return FNB_OK;
 }
 
+// Host-buffer search.  Per replica the call takes a lane (stream + counters + staging) from the replica's pool, so
+// concurrent callers proceed side by side.  Three ways for the bytes to travel, chosen per call:
+//   * caller buffers are page-locked (cudaHostAlloc / cudaHostRegister, e.g. torch pinned tensors): used in place — the
+//     kernel reads each query straight from host memory when a warp picks it up and writes the K results straight
+//     back, so the transfers overlap the traversal instead of bracketing it;
+//   * pageable buffers (what a numpy caller of the reference binding passes) up to FNB_STAGE_MAX bytes: the host copies
+//     the queries chunk by chunk into the lane's pinned block WHILE the kernel runs — the kernel is launched after the
+//     first chunk and every warp waits for a watermark (system-scope release / acquire) to pass its query — and the
+//     kernel writes the results into the pinned block, from where they are copied out after the launch;
+//   * anything larger: asynchronous copies through a device workspace on the lane's stream.
 int fnb_search(fnb_index* ix, const void* queries, int64_t Q, int K, int ef_search, int num_initializations,
                float* out_dist, int32_t* out_label, fnb_search_stats* stats) {
   if (!ix) return fail(FNB_ERR_INVALID_ARG, "index is NULL");
+  SharedLock lock(ix->mu);
   SearchParams p0;
   const int64_t n_rep = ix->replicas.empty() ? 1 : (int64_t)ix->replicas.size();
   int rc = plan_search(ix, Q, K, ef_search, num_initializations, &p0, (Q + n_rep - 1) / n_rep);
@@ -485,15 +655,13 @@ int fnb_search(fnb_index* ix, const void* queries, int64_t Q, int K, int ef_sear
   if (stats) memset(stats, 0, sizeof(*stats));
   if (Q == 0) return FNB_OK;
   if (!queries || !out_dist || !out_label) return fail(FNB_ERR_INVALID_ARG, "NULL buffer");
-  std::lock_guard<std::mutex> lock(ix->mu);
   const Header& h = ix->h;
   const int R = (int)ix->replicas.size();
-  int prev = 0;
-  cudaGetDevice(&prev);
-  // Page-locked caller buffers (cudaHostAlloc / cudaHostRegister, e.g. torch pinned tensors) are used in place:
-  // the kernel reads each query straight from host memory when a warp picks it up and writes the K results
-  // straight back, so the transfers overlap the traversal instead of bracketing it.  Pageable buffers are
-  // staged through device memory with asynchronous copies on the replica's stream.
+  DeviceScope scope;
+  static const bool no_zero_copy = getenv("FNB_NO_ZEROCOPY") != nullptr;
+  static const bool no_staging = getenv("FNB_NO_STAGING") != nullptr;
+  static const bool no_feed = getenv("FNB_NO_FEED") != nullptr;
+  static const size_t stage_max = getenv("FNB_STAGE_MAX") ? (size_t)atoll(getenv("FNB_STAGE_MAX")) : ((size_t)64 << 20);
   auto mapped = [](const void* host) -> unsigned char* {
     cudaPointerAttributes a;
     if (cudaPointerGetAttributes(&a, host) != cudaSuccess) {
@@ -502,102 +670,125 @@ int fnb_search(fnb_index* ix, const void* queries, int64_t Q, int K, int ef_sear
     }
     return a.type == cudaMemoryTypeHost ? static_cast<unsigned char*>(a.devicePointer) : nullptr;
   };
-  unsigned char* zq = getenv("FNB_NO_ZEROCOPY") ? nullptr : mapped(queries);
-  unsigned char* zd = getenv("FNB_NO_ZEROCOPY") ? nullptr : mapped(out_dist);
-  unsigned char* zl = getenv("FNB_NO_ZEROCOPY") ? nullptr : mapped(out_label);
+  unsigned char* zq = no_zero_copy ? nullptr : mapped(queries);
+  unsigned char* zd = no_zero_copy ? nullptr : mapped(out_dist);
+  unsigned char* zl = no_zero_copy ? nullptr : mapped(out_label);
   if (!zd || !zl) zd = zl = nullptr;
   const int64_t per = (Q + R - 1) / R;
   struct Part {
-    int64_t q0, nq;
-    unsigned char *d_q, *d_dist, *d_label;
-    bool staged;  // small batch: everything goes through the replica's pinned staging block, no copies on the stream
-    size_t off_dist, off_label, off_nd, off_nh, off_len;
+    int64_t q0 = 0, nq = 0;
+    bool stage_out = false, counters_in_block = false;
+    size_t off_dist = 0, off_label = 0, off_nd = 0, off_nh = 0, off_len = 0;
   };
   std::vector<Part> parts(R);
+  std::vector<LaneHold> held;
+  held.reserve(R);
   // enqueue everything on every replica first, then wait: replicas run concurrently from one host thread
   for (int i = 0; i < R; i++) {
     Replica& r = ix->replicas[i];
     Part& pt = parts[i];
     pt.q0 = std::min<int64_t>(Q, per * i);
     pt.nq = std::min<int64_t>(Q, per * (i + 1)) - pt.q0;
-    pt.staged = false;
+    held.emplace_back();
     if (pt.nq <= 0) continue;
     CU(cudaSetDevice(r.device));
+    LaneHold& hold = held.back();
+    hold.r = &r;
+    rc = acquire_lane(r, &hold.l);
+    if (rc != FNB_OK) return rc;
+    Lane& ln = *hold.l;
     const size_t qb = (size_t)pt.nq * h.data_size, ob = (size_t)pt.nq * K * 4, cb = (size_t)pt.nq * 4;
+    const unsigned char* q_src = (const unsigned char*)queries + (size_t)pt.q0 * h.data_size;
     SearchParams p = p0;
     p.Q = (uint32_t)pt.nq;
     p.vec = r.vec;
     p.adj = r.adj;
     p.labels = r.labels;
     p.lat = choose_latency_variant(pt.nq, r.num_sms);
-    // Small batches (search_single above all) are bounded by host and launch overhead, not by the kernel: the
-    // queries are copied by the CPU into a pinned block the kernel reads in place, results and per-query counters
-    // are written by the kernel straight into that block (plain stores, no device totals to clear or fetch), and
-    // the only things on the stream are the kernel and the two events that time it.
-    pt.staged = p.lat && !getenv("FNB_NO_STAGING") && qb + 2 * ob + 3 * cb <= (size_t)(1u << 20);
-    if (pt.staged) {
-      pt.off_dist = align256(qb);
-      pt.off_label = pt.off_dist + align256(ob);
-      pt.off_nd = pt.off_label + align256(ob);
-      pt.off_nh = pt.off_nd + align256(cb);
-      pt.off_len = pt.off_nh + align256(cb);
-      rc = ensure_workspace(&r, 0, pt.off_len + align256(cb));
-      if (rc != FNB_OK) {
-        cudaSetDevice(prev);
-        return rc;
-      }
-      memcpy(r.h_pinned, (const unsigned char*)queries + (size_t)pt.q0 * h.data_size, qb);
-      unsigned char* dp = r.h_pinned_dev;
-      p.queries = dp;
-      p.out_dist = reinterpret_cast<float*>(dp + pt.off_dist);
-      p.out_label = reinterpret_cast<int32_t*>(dp + pt.off_label);
+    // layout of the lane's pinned block: [queries (small batches only) | dist | label | per-query counters (lat only)]
+    pt.counters_in_block = p.lat != 0;  // small batches: per-query counters by plain stores, no device totals to clear / fetch
+    // queries of a pageable caller.  Small batch (latency variant): copied by the CPU into the pinned block the kernel
+    // reads in place — nothing but the kernel on the stream.  Large batch: FED through the device workspace in chunks
+    // on the lane's copy stream while the kernel already runs (the throughput variant hands queries out in index
+    // order and every warp waits for the watermark to pass its query).
+    const bool q_in_block = !zq && p.lat && !no_staging;
+    const bool feed = !zq && !q_in_block && !no_feed && qb >= ((size_t)1 << 20);
+    pt.off_dist = q_in_block ? align256(qb) : 0;
+    pt.off_label = pt.off_dist + (zd ? 0 : align256(ob));
+    pt.off_nd = pt.off_label + (zd ? 0 : align256(ob));
+    pt.off_nh = pt.off_nd + (pt.counters_in_block ? align256(cb) : 0);
+    pt.off_len = pt.off_nh + (pt.counters_in_block ? align256(cb) : 0);
+    const size_t block = pt.off_len + (pt.counters_in_block ? align256(cb) : 0);
+    pt.stage_out = !zd && !no_staging && block <= stage_max;
+    const bool need_block = q_in_block || pt.stage_out || pt.counters_in_block;
+    const size_t ws_q = (!zq && !q_in_block) ? align256(qb) : 0;
+    rc = ensure_workspace(&ln, ws_q + (!zd && !pt.stage_out ? 2 * align256(ob) : 0) + 256, need_block ? block : 0);
+    if (rc != FNB_OK) return rc;
+    unsigned char* dp = ln.h_pinned_dev;
+    unsigned char *d_q, *d_dist, *d_label;
+    if (zq) d_q = zq + (size_t)pt.q0 * h.data_size;
+    else if (q_in_block) d_q = dp;
+    else d_q = ln.ws;
+    if (zd) {
+      d_dist = zd + (size_t)pt.q0 * K * 4;
+      d_label = zl + (size_t)pt.q0 * K * 4;
+    } else if (pt.stage_out) {
+      d_dist = dp + pt.off_dist;
+      d_label = dp + pt.off_label;
+    } else {
+      d_dist = ln.ws + ws_q;
+      d_label = d_dist + align256(ob);
+    }
+    p.queries = d_q;
+    if (((uintptr_t)d_q & 15u) != 0) p.query_vec_ok = 0;
+    p.out_dist = reinterpret_cast<float*>(d_dist);
+    p.out_label = reinterpret_cast<int32_t*>(d_label);
+    if (pt.counters_in_block) {
       p.out_ndist = reinterpret_cast<uint32_t*>(dp + pt.off_nd);
       p.out_nhops = reinterpret_cast<uint32_t*>(dp + pt.off_nh);
       p.out_len = reinterpret_cast<uint32_t*>(dp + pt.off_len);
       p.counter = nullptr;
       p.totals = nullptr;
-      CU(cudaEventRecord(r.ev[1], r.stream));
-      cudaError_t e = dispatch_search(ix, p, r.num_sms, r.stream);
-      if (e != cudaSuccess) {
-        cudaSetDevice(prev);
-        return fail(FNB_ERR_CUDA, "search kernel launch failed: %s", cudaGetErrorString(e));
+    } else {
+      p.counter = ln.counter;
+      p.totals = ln.totals;
+    }
+    if (q_in_block) memcpy(ln.h_pinned, q_src, qb);
+    if (feed) p.q_ready = ln.q_ready;
+    CU(cudaEventRecord(ln.ev[0], ln.stream));
+    if (!zq && !q_in_block && !feed) CU(cudaMemcpyAsync(d_q, q_src, qb, cudaMemcpyHostToDevice, ln.stream));
+    if (!pt.counters_in_block) CU(cudaMemsetAsync(ln.counter, 0, 128, ln.stream));  // counter, watermark, totals
+    if (feed) {
+      CU(cudaEventRecord(ln.ev_feed, ln.stream));  // the first watermark must not land before the clear above
+      CU(cudaStreamWaitEvent(ln.copy_stream, ln.ev_feed, 0));
+    }
+    CU(cudaEventRecord(ln.ev[1], ln.stream));
+    cudaError_t e = dispatch_search(ix, p, r.num_sms, ln.stream);
+    if (e != cudaSuccess) return fail(FNB_ERR_CUDA, "search kernel launch failed: %s", cudaGetErrorString(e));
+    CU(cudaEventRecord(ln.ev[2], ln.stream));
+    if (!zd && !pt.stage_out) {
+      CU(cudaMemcpyAsync(out_dist + (size_t)pt.q0 * K, d_dist, ob, cudaMemcpyDeviceToHost, ln.stream));
+      CU(cudaMemcpyAsync(out_label + (size_t)pt.q0 * K, d_label, ob, cudaMemcpyDeviceToHost, ln.stream));
+    }
+    if (!pt.counters_in_block) CU(cudaMemcpyAsync(ln.h_totals, ln.totals, 24, cudaMemcpyDeviceToHost, ln.stream));
+    CU(cudaEventRecord(ln.ev[3], ln.stream));
+    if (feed) {
+      // a pageable cudaMemcpyAsync returns once the chunk is staged, so this loop paces itself against the host copy
+      // while the DMA of earlier chunks and the traversal of the queries already there proceed
+      hold.feeding = true;
+      const size_t chunk_q = std::max<size_t>(((size_t)pt.nq + FNB_FEED_CHUNKS - 1) / FNB_FEED_CHUNKS,
+                                              std::max<size_t>(64, ((size_t)256 << 10) / h.data_size));
+      size_t fed = 0;
+      for (int c = 0; fed < (size_t)pt.nq; c++) {
+        const size_t n = std::min(chunk_q, (size_t)pt.nq - fed);
+        CU(cudaMemcpyAsync(d_q + fed * h.data_size, q_src + fed * h.data_size, n * h.data_size, cudaMemcpyHostToDevice,
+                           ln.copy_stream));
+        fed += n;
+        ln.h_marks[c] = (uint32_t)fed;
+        CU(cudaMemcpyAsync(ln.q_ready, ln.h_marks + c, 4, cudaMemcpyHostToDevice, ln.copy_stream));
       }
-      CU(cudaEventRecord(r.ev[2], r.stream));
-      continue;
+      hold.feeding = false;
     }
-    rc = ensure_workspace(&r, (zq ? 0 : align256(qb)) + (zd ? 0 : 2 * align256(ob)) + 256, 0);
-    if (rc != FNB_OK) {
-      cudaSetDevice(prev);
-      return rc;
-    }
-    pt.d_q = zq ? zq + (size_t)pt.q0 * h.data_size : r.ws;
-    pt.d_dist = zd ? zd + (size_t)pt.q0 * K * 4 : r.ws + (zq ? 0 : align256(qb));
-    pt.d_label = zd ? zl + (size_t)pt.q0 * K * 4 : pt.d_dist + align256(ob);
-    p.queries = pt.d_q;
-    if (((uintptr_t)pt.d_q & 15u) != 0) p.query_vec_ok = 0;
-    p.out_dist = reinterpret_cast<float*>(pt.d_dist);
-    p.out_label = reinterpret_cast<int32_t*>(pt.d_label);
-    p.counter = r.counter;
-    p.totals = r.totals;
-    CU(cudaEventRecord(r.ev[0], r.stream));
-    if (!zq)
-      CU(cudaMemcpyAsync(pt.d_q, (const unsigned char*)queries + (size_t)pt.q0 * h.data_size, qb,
-                         cudaMemcpyHostToDevice, r.stream));
-    if (!p.lat) CU(cudaMemsetAsync(r.counter, 0, 4, r.stream));
-    CU(cudaMemsetAsync(r.totals, 0, 24, r.stream));
-    CU(cudaEventRecord(r.ev[1], r.stream));
-    cudaError_t e = dispatch_search(ix, p, r.num_sms, r.stream);
-    if (e != cudaSuccess) {
-      cudaSetDevice(prev);
-      return fail(FNB_ERR_CUDA, "search kernel launch failed: %s", cudaGetErrorString(e));
-    }
-    CU(cudaEventRecord(r.ev[2], r.stream));
-    if (!zd) {
-      CU(cudaMemcpyAsync(out_dist + (size_t)pt.q0 * K, pt.d_dist, ob, cudaMemcpyDeviceToHost, r.stream));
-      CU(cudaMemcpyAsync(out_label + (size_t)pt.q0 * K, pt.d_label, ob, cudaMemcpyDeviceToHost, r.stream));
-    }
-    CU(cudaMemcpyAsync(r.h_totals, r.totals, 24, cudaMemcpyDeviceToHost, r.stream));
-    CU(cudaEventRecord(r.ev[3], r.stream));
   }
   int64_t nd = 0, nh = 0, ns = 0;
   float kms = 0.f, tms = 0.f;
@@ -606,35 +797,37 @@ int fnb_search(fnb_index* ix, const void* queries, int64_t Q, int K, int ef_sear
     const Part& pt = parts[i];
     if (pt.nq <= 0) continue;
     Replica& r = ix->replicas[i];
+    Lane& ln = *held[i].l;
     CU(cudaSetDevice(r.device));
-    CU(cudaStreamSynchronize(r.stream));
+    CU(cudaStreamSynchronize(ln.stream));
     float a = 0.f, b = 0.f;
-    CU(cudaEventElapsedTime(&a, r.ev[1], r.ev[2]));
-    if (pt.staged) {
+    CU(cudaEventElapsedTime(&a, ln.ev[1], ln.ev[2]));
+    CU(cudaEventElapsedTime(&b, ln.ev[0], ln.ev[3]));
+    if (pt.stage_out) {
       const size_t ob = (size_t)pt.nq * K * 4;
-      memcpy(out_dist + (size_t)pt.q0 * K, r.h_pinned + pt.off_dist, ob);
-      memcpy(out_label + (size_t)pt.q0 * K, r.h_pinned + pt.off_label, ob);
-      const uint32_t* c_nd = reinterpret_cast<const uint32_t*>(r.h_pinned + pt.off_nd);
-      const uint32_t* c_nh = reinterpret_cast<const uint32_t*>(r.h_pinned + pt.off_nh);
-      const uint32_t* c_len = reinterpret_cast<const uint32_t*>(r.h_pinned + pt.off_len);
+      memcpy(out_dist + (size_t)pt.q0 * K, ln.h_pinned + pt.off_dist, ob);
+      memcpy(out_label + (size_t)pt.q0 * K, ln.h_pinned + pt.off_label, ob);
+    }
+    if (pt.counters_in_block) {
+      const uint32_t* c_nd = reinterpret_cast<const uint32_t*>(ln.h_pinned + pt.off_nd);
+      const uint32_t* c_nh = reinterpret_cast<const uint32_t*>(ln.h_pinned + pt.off_nh);
+      const uint32_t* c_len = reinterpret_cast<const uint32_t*>(ln.h_pinned + pt.off_len);
       for (int64_t q = 0; q < pt.nq; q++) {
         nd += c_nd[q];
         nh += c_nh[q];
         ns += c_len[q] < (uint32_t)K ? 1 : 0;
       }
-      b = a;
     } else {
-      const unsigned long long* t = r.h_totals;
+      const unsigned long long* t = ln.h_totals;
       nd += (int64_t)t[0];
       nh += (int64_t)t[1];
       ns += (int64_t)t[2];
-      CU(cudaEventElapsedTime(&b, r.ev[0], r.ev[3]));
     }
     kms = std::max(kms, a);
     tms = std::max(tms, b);
     launches++;
   }
-  cudaSetDevice(prev);
+  held.clear();  // lanes back to their pools
   if (stats) {
     stats->n_queries = Q;
     stats->n_dist = nd;

@@ -3,7 +3,10 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+#include <condition_variable>
 #include <mutex>
+#include <shared_mutex>
 #include <string>
 #include <vector>
 
@@ -20,6 +23,38 @@ struct Header {
   uint64_t M = 0, data_size = 0, node_size = 0, max_nodes = 0, cur_nodes = 0, dim = 0;
 };
 
+// One search in flight: everything a host-buffer search call needs besides the index arrays.  A replica keeps a pool of
+// lanes so that concurrent callers of fnb_search (the reference's Index::search is re-entrant, Index.h:387-409 with
+// VisitedSetPool.h:154-172 handing every thread its own visited set) run side by side on their own streams.
+struct Lane {
+  cudaStream_t stream = nullptr;
+  unsigned int* counter = nullptr;         // device: persistent-warp work counter
+  unsigned long long* totals = nullptr;    // device: [3] n_dist, n_hops, short results
+  unsigned int* q_ready = nullptr;         // device: watermark of a host-fed batch (queries already copied in)
+  unsigned long long* h_totals = nullptr;  // pinned mirror of `totals`
+  uint32_t* h_marks = nullptr;             // pinned: the watermark values a host-fed batch copies to q_ready, [FNB_FEED_CHUNKS + 1]
+  cudaStream_t copy_stream = nullptr;      // feeds the queries of a pageable caller while the kernel runs on `stream`
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_feed = nullptr;
+  unsigned char* ws = nullptr;  // device workspace: queries of pageable callers, results too large for the pinned block
+  size_t ws_bytes = 0;
+  unsigned char* h_pinned = nullptr;      // pinned block the kernel writes results / per-query counters into
+  unsigned char* h_pinned_dev = nullptr;  // its device-side alias
+  size_t h_pinned_bytes = 0;
+};
+
+#define FNB_FEED_CHUNKS 48
+#define FNB_RING_SLOTS 256u  // per-call {counter, totals} slots of fnb_search_device (64 B each)
+
+struct LanePool {
+  std::mutex mu;
+  std::condition_variable cv;
+  std::vector<Lane*> all, idle;
+  int max_lanes = 16;
+  unsigned char* ring = nullptr;  // device: FNB_RING_SLOTS x 64 B
+  std::atomic<uint32_t> ring_seq{0};
+};
+
 // One full copy of the index in the HBM of one device, plus the per-device launch state.
 struct Replica {
   int device = -1;
@@ -27,16 +62,12 @@ struct Replica {
   uint4* vec = nullptr;
   uint32_t* adj = nullptr;
   int32_t* labels = nullptr;
+  // stream / counters of the mutating entry points (construction, re-ordering, brute force): used under the
+  // exclusive index lock only
   unsigned int* counter = nullptr;
   unsigned long long* totals = nullptr;
-  unsigned long long* h_totals = nullptr;  // pinned mirror of `totals`
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-  unsigned char* ws = nullptr;  // device workspace of the host-buffer entry points
-  size_t ws_bytes = 0;
-  unsigned char* h_pinned = nullptr;      // pinned staging block of the small-batch path
-  unsigned char* h_pinned_dev = nullptr;  // its device-side alias
-  size_t h_pinned_bytes = 0;
+  LanePool* pool = nullptr;  // search lanes (shared index lock)
   uint64_t device_bytes = 0;
   uint64_t capacity = 0;  // rows the vec / adj / labels arrays can hold (>= cur_nodes; construction grows it)
 };
@@ -46,12 +77,27 @@ extern thread_local std::string g_last_error;
 
 }  // namespace fnb
 
+struct fnb_build_scratch;  // build.cu
+void fnb_build_scratch_free(fnb_build_scratch* b);
+struct fnb_label_map;  // rerank.cu
+void fnb_label_map_free(fnb_label_map* m);
+struct fnb_index;
+// Caches derived from the graph (construction degrees, label table) are dropped by whoever edits it; the caller holds
+// the exclusive index lock.  links: link rows changed outside fnb_index_add; labels: labels / node numbering changed.
+void fnb_index_mutated(fnb_index* ix, bool links, bool labels);
+
 struct fnb_index {
   fnb::Header h;
   uint32_t nchunks = 0, stride = 0;
   int G = 8;
   std::vector<fnb::Replica> replicas;
-  std::mutex mu;
+  fnb_build_scratch* build = nullptr;  // construction scratch kept between fnb_index_add calls (single-device index)
+  fnb_label_map* label_map = nullptr;  // label -> node table of fnb_rerank, built on first use
+  std::mutex aux_mu;                   // guards label_map creation among concurrent (shared-lock) callers
+  // searches (fnb_search, fnb_search_device, save, info) hold it shared; everything that changes the graph or the
+  // device arrays (add, reserve, allocate_nodes, build_graph_links, relabel, reorder) and brute force hold it
+  // exclusively and first wait for every kernel still in flight on the index's devices (fnb::quiesce)
+  mutable std::shared_mutex mu;
 };
 
 // build.cu: host vectors -> padded rows [cur_nodes, cur_nodes + n), labels (NULL: label_base, label_base + 1, ...),
@@ -60,7 +106,13 @@ int upload_new_rows_locked(fnb_index* ix, const void* vectors, const int32_t* la
                            bool init_links);
 
 namespace fnb {
-int plan_search(const fnb_index* ix, int64_t Q, int K, int ef, int ninit, SearchParams* p, int64_t launch_q = 0);
+typedef std::unique_lock<std::shared_mutex> ExclusiveLock;
+typedef std::shared_lock<std::shared_mutex> SharedLock;
+// after taking the exclusive lock: wait for asynchronous searches (fnb_search_device on caller streams) still in flight
+void quiesce(fnb_index* ix);
+// n_nodes != 0: search only the first n_nodes nodes (construction: the graph a batch is inserted into)
+int plan_search(const fnb_index* ix, int64_t Q, int K, int ef, int ninit, SearchParams* p, int64_t launch_q = 0,
+                uint64_t n_nodes = 0);
 cudaError_t dispatch_search(const fnb_index* ix, const SearchParams& p, int num_sms, cudaStream_t s);
 cudaError_t dispatch_search_f32(const fnb_index* ix, const SearchParams& p, int num_sms, cudaStream_t s);
 cudaError_t dispatch_search_u8(const fnb_index* ix, const SearchParams& p, int num_sms, cudaStream_t s);

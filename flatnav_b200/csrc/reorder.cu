@@ -383,6 +383,7 @@ extern "C" {
 
 int fnb_index_links(const fnb_index* ix, uint32_t* out_links) {
   if (!ix || !out_links) return fail(FNB_ERR_INVALID_ARG, "NULL argument");
+  fnb::ExclusiveLock lock(ix->mu);  // download_links runs on the mutator stream
   std::vector<uint32_t> links;
   int rc = download_links(ix, &links);
   if (rc != FNB_OK) return rc;
@@ -392,8 +393,11 @@ int fnb_index_links(const fnb_index* ix, uint32_t* out_links) {
 
 int fnb_index_relabel(fnb_index* ix, const uint32_t* perm) {
   if (!ix || !perm) return fail(FNB_ERR_INVALID_ARG, "NULL argument");
-  std::lock_guard<std::mutex> lock(ix->mu);
-  return apply_perm(ix, perm);
+  fnb::ExclusiveLock lock(ix->mu);
+  fnb::quiesce(ix);
+  const int rc = apply_perm(ix, perm);
+  fnb_index_mutated(ix, true, true);
+  return rc;
 }
 
 int fnb_graph_order(const uint32_t* links, uint64_t n_nodes, uint64_t max_edges_per_node, int method, int window,
@@ -419,7 +423,8 @@ int fnb_index_reorder(fnb_index* ix, int method, int window, uint32_t* perm_out)
   if (method != FNB_REORDER_GORDER && method != FNB_REORDER_RCM)
     return fail(FNB_ERR_INVALID_ARG, "Invalid reordering method: %d", method);  // Index.h:421-423
   if (window <= 0) window = 5;                                                   // Index.h:418
-  std::lock_guard<std::mutex> lock(ix->mu);
+  fnb::ExclusiveLock lock(ix->mu);
+  fnb::quiesce(ix);
   std::vector<uint32_t> links, perm;
   int rc = download_links(ix, &links);
   if (rc != FNB_OK) return rc;
@@ -427,6 +432,7 @@ int fnb_index_reorder(fnb_index* ix, int method, int window, uint32_t* perm_out)
   rc = method == FNB_REORDER_GORDER ? gorder_perm(links.data(), n, M, window, &perm) : rcm_perm(links.data(), n, M, &perm);
   if (rc != FNB_OK) return rc;
   rc = apply_perm(ix, perm.data());
+  fnb_index_mutated(ix, true, true);
   if (rc != FNB_OK) return rc;
   if (perm_out && n) memcpy(perm_out, perm.data(), (size_t)n * 4);
   return FNB_OK;
@@ -438,7 +444,8 @@ int fnb_index_allocate_nodes(fnb_index* ix, const void* vectors, const int32_t* 
   if (n == 0) return FNB_OK;
   if (!vectors) return fail(FNB_ERR_INVALID_ARG, "vectors is NULL");
   if (ix->replicas.size() != 1) return fail(FNB_ERR_UNSUPPORTED, "construction works on a single-device index");
-  std::lock_guard<std::mutex> lock(ix->mu);
+  fnb::ExclusiveLock lock(ix->mu);
+  fnb::quiesce(ix);
   Header& h = ix->h;
   Replica& r = ix->replicas[0];
   if (h.cur_nodes + (uint64_t)n > h.max_nodes || h.cur_nodes + (uint64_t)n > r.capacity)
@@ -448,6 +455,7 @@ int fnb_index_allocate_nodes(fnb_index* ix, const void* vectors, const int32_t* 
   int rc = upload_new_rows_locked(ix, vectors, labels, (int32_t)h.cur_nodes, n, /*init_links=*/true);
   if (rc != FNB_OK) return rc;
   h.cur_nodes += (uint64_t)n;
+  fnb_index_mutated(ix, true, true);
   return FNB_OK;
 }
 
@@ -456,7 +464,8 @@ int fnb_index_build_graph_links(fnb_index* ix, const char* mtx_filename) {
   if (ix->replicas.size() != 1) return fail(FNB_ERR_UNSUPPORTED, "construction works on a single-device index");
   std::ifstream in(mtx_filename);
   if (!in.is_open()) return fail(FNB_ERR_IO, "Unable to open file for reading: %s", mtx_filename);
-  std::lock_guard<std::mutex> lock(ix->mu);
+  fnb::ExclusiveLock lock(ix->mu);
+  fnb::quiesce(ix);
   const Header& h = ix->h;
   std::string line;
   while (std::getline(in, line)) {  // skip the '%' header lines; the first other line is the size line
@@ -505,6 +514,7 @@ int fnb_index_build_graph_links(fnb_index* ix, const char* mtx_filename) {
   R_CU(cudaStreamSynchronize(r.stream));
   for (void* ptr : tmp) cudaFree(ptr);
   cudaSetDevice(prev);
+  fnb_index_mutated(ix, true, false);
   return FNB_OK;
 }
 

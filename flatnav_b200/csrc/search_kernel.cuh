@@ -59,7 +59,13 @@ __host__ __device__ constexpr int fnb_min_ctas(int ch) {
 // queries are 2.8 waves of 3552 warps) the last, partly filled wave costs more with more slots than the extra
 // residency earns, so the host picks the plan per launch from the batch size (choose_dense_plan).
 #define FNB_CTAS_DENSE 7
-__host__ __device__ constexpr int fnb_batches_in_flight(int ch) { return ch >= 4 ? 1 : 4 / ch; }
+#ifndef FNB_U_CH4
+#define FNB_U_CH4 1
+#endif
+#ifndef FNB_U_CH2
+#define FNB_U_CH2 2
+#endif
+__host__ __device__ constexpr int fnb_batches_in_flight(int ch) { return ch >= 4 ? FNB_U_CH4 : (ch == 2 ? FNB_U_CH2 : 4 / ch); }
 // Latency variant (few queries, one warp per CTA, registers are free): hold as many warp-wide load batches in
 // registers as ~96 staging registers allow, up to all 32 rows of an expansion, so that one hop costs ONE HBM round
 // trip for its rows instead of one per batch.
@@ -95,6 +101,9 @@ struct SearchParams {
                                 // the new nodes' own rows); chunks beyond the data are zero there
   uint32_t dense;  // 1 => the 28-warps-per-SM instantiation (large batches of short rows; never with lat)
   uint32_t lat;  // 1 => latency variant (few queries): one warp per CTA, query = blockIdx.x (grid-stride), `counter` unused
+  // != null => the queries are still being copied into device memory while the kernel runs (fnb_search with pageable
+  // caller buffers): *q_ready = number of leading queries already in place; a warp waits for it to pass its query index
+  const unsigned int* q_ready;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -117,6 +126,28 @@ __device__ __forceinline__ uint4 ldg_stream_if(const uint4* p, bool pred) {
   return r;
 }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// Host-fed batches (fnb_search with pageable caller buffers): the queries are still being copied into device memory
+// while the kernel runs; *q_ready is the number of leading queries already in place (device memory, written by the
+// copy engine after each chunk, in stream order).
+//
+// Wait until *q_ready > qi.  Written as ONE block of PTX on purpose: as a C++ loop (any flavour: acquire load in inline
+// asm + __nanosleep, out-of-line call) it made ptxas spill 72 ... 152 bytes in the traversal loop of the 512-byte-row
+// instantiations and grow their code by half; as an opaque block it costs nothing.  Bounded (~10 s of 500 ns naps): if
+// the feeding thread died the warp goes on with whatever is there and the call fails on the host side.
+__device__ __forceinline__ void feed_wait(const unsigned int* p, uint32_t qi) {
+  asm volatile(
+      "{\n\t.reg .pred pw;\n\t.reg .u32 rv, rc;\n\t"
+      "mov.u32 rc, 0;\n\t"
+      "FNB_FEED_WAIT_%=:\n\t"
+      "ld.acquire.gpu.global.u32 rv, [%0];\n\t"
+      "add.u32 rc, rc, 1;\n\t"
+      "setp.ls.u32 pw, rv, %1;\n\t"
+      "setp.lt.and.u32 pw, rc, 20000000, pw;\n\t"
+      "@pw nanosleep.u32 500;\n\t"
+      "@pw bra FNB_FEED_WAIT_%=;\n\t}" ::"l"(p),
+      "r"(qi)
+      : "memory");
+}
 
 __device__ __forceinline__ uint32_t ord_f32(float f) {
   uint32_t u = __float_as_uint(f);
@@ -222,7 +253,7 @@ __device__ __forceinline__ uint4 load_query_chunk(const SearchParams& p, uint32_
   if (p.query_pitch_chunks) return __ldg(reinterpret_cast<const uint4*>(p.queries) + (size_t)qi * p.query_pitch_chunks + chunk);
   if (p.query_vec_ok) {
     const uint4* row = reinterpret_cast<const uint4*>(p.queries) + (size_t)qi * p.nchunks;
-    return __ldg(row + chunk);
+    return __ldcg(row + chunk);  // L2 only: a query row is read once, and a host-fed batch changes under the kernel
   }
   if (DT == DT_F32) {
     const float* row = reinterpret_cast<const float*>(p.queries) + (size_t)qi * p.dim;
@@ -520,6 +551,7 @@ __global__ void __launch_bounds__(LAT ? 32 : FNB_WARPS_PER_CTA * 32, LAT ? 1 : (
       qi = __shfl_sync(FNB_FULL, qi, 0);
     }
     if (qi >= p.Q) break;
+    if (!LAT && p.q_ready) feed_wait(p.q_ready, qi);  // host-fed batch: query qi may still be on its way
 
     uint4 q[CH];
 #pragma unroll

@@ -132,6 +132,15 @@ class DatasetShardedSearcher:
             _capi.lib().fnb_exchange_free(self._ex)
             self._ex = None
 
+    def check_status(self) -> None:
+        """After a synchronise: raises if a peer never delivered its lists to this rank (peer exchange only)."""
+        if self._ex is not None:
+            import torch
+
+            from . import _capi
+            torch.cuda.synchronize()
+            _capi.check(_capi.lib().fnb_exchange_status(self._ex))
+
     def search_device(self, d_queries: int, Q: int, K: int, ef_search: int, num_initializations: int, d_out_dist: int,
                       d_out_label: int, stream: int = 0) -> None:
         """Collective, asynchronous: raw device pointers in, global top-K [Q, K] out (peer-memory path)."""

@@ -81,14 +81,26 @@ class _GpuIndex:
         # py::array_t<T, c_style | forcecast>  (bindings.cpp:36-51)
         return np.ascontiguousarray(a, dtype=_NP[self._data_type])
 
-    def search(self, queries, K: int, ef_search: int, num_initializations: int = 100, *, out=None):
+    def search(self, queries, K: int, ef_search: int, num_initializations: int = 100, *, out=None,
+               exact_rerank: bool = False):
         """PyIndex::search -> searchImpl (bindings.cpp:337-345, 161-228).
 
         Returns (distances float32 [Q,K], labels int32 [Q,K]).  `out` (extension): a pair of preallocated
-        C-contiguous arrays of those shapes/dtypes (e.g. pinned memory) to write into instead of fresh ones."""
+        C-contiguous arrays of those shapes/dtypes (e.g. pinned memory) to write into instead of fresh ones.
+        `exact_rerank` (extension): take the whole max(ef_search, K)-long candidate list of the
+        traversal and re-rank it with `rerank` before cutting to K.  The traversal already evaluates exact distances,
+        so this returns what the plain call returns (a property the tests pin); it exists for pipelines whose first
+        stage is approximate and for protocol parity with drivers that re-rank."""
         q = self._cast(queries)
         if q.ndim != 2 or q.shape[1] != self._dim:
             raise ValueError("Queries have incorrect dimensions.")
+        if exact_rerank:
+            _, cand = self.search(q, max(int(ef_search), int(K)), ef_search, num_initializations)
+            d, l = self.rerank(q, cand, K)
+            if out is not None:
+                out[0][...], out[1][...] = d, l
+                return out
+            return d, l
         Q = q.shape[0]
         if out is not None:
             dist, lab = out
@@ -131,6 +143,24 @@ class _GpuIndex:
         _capi.check(rc)
         return dist, lab
 
+    def rerank(self, queries, candidates, K: int, candidates_are_labels: bool = True):
+        """Exact re-rank (extension): for every query the candidate labels (or node ids) of
+        `candidates[q]` (int array [Q, C]) are evaluated exactly and the K best by (distance, node id) returned as
+        (distances float32 [Q,K], labels int32 [Q,K]); unknown / negative / repeated candidates are skipped, unfilled
+        slots are +inf / -1."""
+        q = self._cast(queries)
+        if q.ndim != 2 or q.shape[1] != self._dim:
+            raise ValueError("Queries have incorrect dimensions.")
+        c = np.ascontiguousarray(candidates, dtype=np.int32)
+        if c.ndim != 2 or c.shape[0] != q.shape[0] or c.shape[1] == 0:
+            raise ValueError("candidates must be an int array of shape (num_queries, num_candidates).")
+        Q = q.shape[0]
+        dist = np.empty((Q, K), dtype=np.float32)
+        lab = np.empty((Q, K), dtype=np.int32)
+        _capi.check(_capi.lib().fnb_rerank(self._h, q.ctypes.data, Q, c.ctypes.data, c.shape[1],
+                                           1 if candidates_are_labels else 0, int(K), dist.ctypes.data, lab.ctypes.data))
+        return dist, lab
+
     def search_device(self, d_queries: int, Q: int, K: int, ef_search: int, num_initializations: int, d_out_dist: int,
                       d_out_label: int, stream: int = 0, d_ndist: int = 0, d_nhops: int = 0, replica: int = 0) -> None:
         """Kernel-only path on device-resident buffers (raw device pointers as ints); asynchronous."""
@@ -142,6 +172,12 @@ class _GpuIndex:
         nd, nh, ns = C.c_int64(), C.c_int64(), C.c_int64()
         _capi.check(_capi.lib().fnb_search_device_totals(self._h, replica, C.byref(nd), C.byref(nh), C.byref(ns)))
         return nd.value, nh.value, ns.value
+
+    def kernel_signature(self, Q: int, K: int, ef_search: int) -> str:
+        """Name of the traversal-kernel instantiation a search of this shape launches (as ncu prints it, no blanks)."""
+        buf = C.create_string_buffer(128)
+        _capi.check(_capi.lib().fnb_search_kernel_signature(self._h, int(Q), int(K), int(ef_search), buf, 128))
+        return buf.value.decode()
 
     # ---- getters / knobs --------------------------------------------------------------------
     def get_query_distance_computations(self) -> int:

@@ -62,6 +62,38 @@ def make(gen: str, n: int, dim: int, *, queries: bool = False, rank: int = 16, s
     return x
 
 
+def make_device(gen: str, n: int, dim: int, *, queries: bool = False, rank: int = 16, sigma: float = 0.1,
+                stream: int = 0, device=None, chunk: int = 1 << 20):
+    """The same laws drawn on the GPU with torch's generator (a torch tensor on `device`): for the large benchmark
+    legs, where the numpy draw of 10M+ rows takes longer than building the graph.  Same mixing matrix as `make`;
+    the random streams differ from numpy's, so `make` and `make_device` give different (equally distributed) rows."""
+    import torch
+    if gen not in GENERATORS:
+        raise ValueError(f"unknown generator {gen!r}; expected one of {GENERATORS}")
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    g = torch.Generator(device=device)
+    g.manual_seed((QUERY_SEED if queries else DATA_SEED) + 7919 * stream)
+    out_dtype = {"latent-u8": torch.uint8, "latent-i8": torch.int8}.get(gen, torch.float32)
+    out = torch.empty((n, dim), dtype=out_dtype, device=device)
+    A = None if gen == "iid" else torch.from_numpy(_mixing(dim, rank)).to(device)
+    s = float(np.sqrt(1.0 + sigma * sigma))
+    for lo in range(0, n, chunk):
+        hi = min(n, lo + chunk)
+        if gen == "iid":
+            x = torch.randn((hi - lo, dim), generator=g, device=device, dtype=torch.float32)
+        else:
+            z = torch.randn((hi - lo, rank), generator=g, device=device, dtype=torch.float32)
+            x = z @ A + sigma * torch.randn((hi - lo, dim), generator=g, device=device, dtype=torch.float32)
+        if gen == "latent-norm":
+            x = x / torch.clamp(torch.linalg.norm(x, dim=1, keepdim=True), min=1e-30)
+        elif gen in ("latent-u8", "latent-i8"):
+            x = torch.clamp(torch.round((x + 4.0 * s) * (255.0 / (8.0 * s))), 0, 255)
+            if gen == "latent-i8":
+                x = x - 128.0
+        out[lo:hi] = x.to(out_dtype)
+    return out
+
+
 def dtype_code(arr_or_dtype) -> str:
     dt = np.dtype(getattr(arr_or_dtype, "dtype", arr_or_dtype))
     return {np.dtype(np.float32): "f32", np.dtype(np.uint8): "u8", np.dtype(np.int8): "i8"}[dt]

@@ -186,9 +186,26 @@ int fnb_search_device(fnb_index* index, int replica, const void* d_queries, int6
                       int num_initializations, float* d_out_dist, int32_t* d_out_label, uint32_t* d_ndist,
                       uint32_t* d_nhops, void* cuda_stream);
 
+/* Measurement aid (no reference equivalent): the name of the traversal-kernel template instantiation a search of this
+ * shape launches on this index, spelled the way ncu / cuobjdump print it without blanks, e.g.
+ * "fnb_search_kernel<0,0,8,4,1,0,0>" (data type, metric, lanes per row, chunks per lane, exact fit, latency variant,
+ * occupancy plan).  bench.py uses it to check that a committed ncu capture is of the kernel it times. */
+int fnb_search_kernel_signature(const fnb_index* index, int64_t Q, int K, int ef_search, char* out, size_t out_capacity);
+
 /* Exact scan over all nodes (ground truth / exact re-rank).  The reference has no brute force of its own;
  * semantics: top-K by (distance, node id), distances in the same arithmetic as fnb_search.  HOST buffers. */
 int fnb_bruteforce(fnb_index* index, const void* queries, int64_t Q, int K, float* out_dist, int32_t* out_label);
+
+/* Exact re-rank of caller-supplied candidates (the reference's benchmark driver,
+ * experiments/run-benchmark.py:38-124, has no re-rank step of its own — extension).  For each of the Q queries (HOST,
+ * row-major [Q, dim] of the index data type) the C entries of candidates[q] (HOST int32 [Q, C]) are evaluated with the
+ * arithmetic of fnb_search — the distance reported for a (query, node) pair is bit-identical across fnb_search,
+ * fnb_bruteforce and fnb_rerank — and the K best by (distance, node id) are returned with their label fields
+ * (float32 / int32 [Q, K]; unfilled slots +inf / -1).  candidates_are_labels != 0: entries are node labels as search
+ * returns them (unknown labels and negative entries are skipped, of equal labels the lowest node id answers);
+ * 0: entries are node ids.  A candidate listed twice counts once. */
+int fnb_rerank(fnb_index* index, const void* queries, int64_t Q, const int32_t* candidates, int C,
+               int candidates_are_labels, int K, float* out_dist, int32_t* out_label);
 
 /* What the last fnb_bruteforce call on this thread did.  Large problems run as a tcgen05 (tensor-core) GEMM
  * over bf16 hi/lo splits of the vectors that only FILTERS candidates, followed by an exact re-rank in the

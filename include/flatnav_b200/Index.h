@@ -16,6 +16,7 @@
 #pragma once
 
 #include <algorithm>
+#include <atomic>
 #include <cstdint>
 #include <iostream>
 #include <limits>
@@ -109,7 +110,7 @@ class Index {
   Index& operator=(const Index&) = delete;
   Index(Index&& o) noexcept
       : _h(o._h), _info(o._info), _num_threads(o._num_threads), _collect_stats(o._collect_stats),
-        _distance_computations(o._distance_computations), _metric_hops(o._metric_hops) {
+        _distance_computations(o._distance_computations.load()), _metric_hops(o._metric_hops.load()) {
     o._h = nullptr;
   }
   Index& operator=(Index&& o) noexcept {
@@ -119,8 +120,8 @@ class Index {
       _info = o._info;
       _num_threads = o._num_threads;
       _collect_stats = o._collect_stats;
-      _distance_computations = o._distance_computations;
-      _metric_hops = o._metric_hops;
+      _distance_computations = o._distance_computations.load();
+      _metric_hops = o._metric_hops.load();
       o._h = nullptr;
     }
     return *this;
@@ -305,8 +306,9 @@ class Index {
   fnb_info _info{};
   uint32_t _num_threads = 1;
   bool _collect_stats = false;
-  uint64_t _distance_computations = 0;
-  uint64_t _metric_hops = 0;
+  // atomics, as in the reference: search() is re-entrant and callers fan it out over threads
+  std::atomic<uint64_t> _distance_computations{0};
+  std::atomic<uint64_t> _metric_hops{0};
 };
 
 }  // namespace flatnav_b200

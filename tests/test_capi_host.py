@@ -108,3 +108,27 @@ def test_cpp_shim_compiles_and_links(tmp_path):
                     "-Wl,-rpath," + os.path.join(ROOT, "flatnav_b200")], check=True)
     r = subprocess.run([exe], capture_output=True)
     assert r.returncode == 2  # usage
+
+
+def _header(dt=9, M=32, data_size=512, node_size=644, max_nodes=10, cur=10, dim=128, ds2=512):
+    return np.int32(dt).tobytes() + np.array([M, data_size, node_size, max_nodes, cur, dim, ds2], dtype=np.uint64).tobytes()
+
+
+@pytest.mark.parametrize("kw", [
+    dict(M=2**62 + 8, node_size=(512 + 4 * (2**62 + 8) + 4) % 2**64),      # 4*M wraps: node_size check would pass
+    dict(M=70000, node_size=512 + 4 * 70000 + 4),                          # beyond what the kernels index
+    dict(dim=2**62, data_size=0, ds2=0, node_size=4 * 32 + 4),             # dim * 4 wraps to 0
+    dict(max_nodes=2**40, cur=2**40),                                      # node count beyond uint32 node ids
+    dict(node_size=2**63, max_nodes=2**31 - 1),                            # node_size * max_nodes would wrap
+    dict(cur=11),                                                          # cur_num_nodes > max_node_count
+    dict(dt=3),                                                            # unknown data type
+], ids=["M-wraps", "M-huge", "dim-wraps", "too-many-nodes", "blob-wraps", "cur>max", "dtype"])
+def test_hostile_headers_are_rejected_before_any_allocation(kw):
+    """a crafted header must fail the checks of parse_header, not wrap its size arithmetic (runs without a device:
+    the header is parsed before the device is touched)"""
+    import ctypes as C
+    blob = _header(**kw) + bytes(644 * 10)
+    out = C.c_void_p()
+    rc = _capi.lib().fnb_index_from_memory(blob, len(blob), _capi.FNB_METRIC_L2, _capi.FNB_DTYPE_ANY, None, 0, C.byref(out))
+    assert rc in (_capi.FNB_ERR_FORMAT, _capi.FNB_ERR_UNSUPPORTED), (rc, _capi.last_error())
+    assert not out.value

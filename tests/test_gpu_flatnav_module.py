@@ -1,0 +1,92 @@
+"""GPU (-m gpu): code written against the reference's Python package runs on `flatnav` here.  The flow and the calls —
+keyword for keyword — are those of the reference's own unit tests (python-bindings/unit_tests/test_index.py:15-36,
+117-150, test_utils.py:12-24, 58-91, test_parallel_insertions.py:9-40), restated because /root/reference does not exist
+on the GPU box; float64 `np.random.rand` data is cast by the binding exactly as there."""
+import os
+
+import numpy as np
+import pytest
+
+import flatnav
+import flatnav_b200
+from flatnav.data_type import DataType
+from flatnav.index import IndexIPFloat, IndexL2Float, create
+
+pytestmark = pytest.mark.gpu
+
+
+def create_index(distance_type, dim, dataset_size, max_edges_per_node):  # test_utils.py:12-24
+    index = create(distance_type=distance_type, dim=dim, dataset_size=dataset_size, max_edges_per_node=max_edges_per_node,
+                   verbose=True)
+    if not (isinstance(index, IndexL2Float) or isinstance(index, IndexIPFloat)):
+        raise RuntimeError("Invalid index.")
+    return index
+
+
+def compute_recall(index, queries, ground_truth, ef_search, k=100):  # test_utils.py:58-91
+    _, top_k_indices = index.search(queries=queries, ef_search=ef_search, K=k)
+    gts = [set(gt) for gt in ground_truth]
+    return float(np.mean([sum(1 for n in row if n in gts[i]) / k for i, row in enumerate(top_k_indices)]))
+
+
+def test_l2_index_random_dataset_like_the_reference_unit_test(tmp_path, capsys):
+    rng = np.random.default_rng(0)
+    training_set = rng.random((30_000, 784))  # float64, like np.random.rand
+    queries = rng.random((500, 784))
+    index = create_index(distance_type="l2", dim=784, dataset_size=len(training_set), max_edges_per_node=32)
+    assert "max_edges_per_node (M): 32" in capsys.readouterr().out  # verbose=True prints the summary
+    assert hasattr(index, "max_edges_per_node") and index.max_edges_per_node == 32
+    index.set_num_threads(os.cpu_count())  # test_parallel_insertions.py:30
+    assert index.num_threads == os.cpu_count()
+    with pytest.raises(ValueError):
+        index.set_num_threads(0)
+    index.add(data=training_set, ef_construction=64)
+    # the reference's test only checks that search runs on random ground truth; here recall is checked for real
+    _, gt = index.bruteforce(queries, 100)
+    assert compute_recall(index=index, queries=queries, ground_truth=gt, ef_search=200) >= 0.85
+    d, l = index.search(queries=queries, ef_search=32, K=10)
+    assert d.dtype == np.float32 and l.dtype == np.int32 and d.shape == (500, 10) and d.flags.owndata is not None
+    d1, l1 = index.search_single(query=queries[3], ef_search=32, K=10)
+    np.testing.assert_array_equal(d1, d[3])
+    np.testing.assert_array_equal(l1, l[3])
+    assert index.get_query_distance_computations() > 0 and index.get_query_distance_computations() == 0
+    with pytest.raises(ValueError, match="Queries have incorrect dimensions"):
+        index.search(queries=queries[:, :-1], ef_search=32, K=10)
+    with pytest.raises(ValueError, match="Query has incorrect dimensions"):
+        index.search_single(query=queries[:2], ef_search=32, K=10)
+    # save -> load_index -> identical results; and the flatnav_b200 package reads the same file with the same answers
+    p = str(tmp_path / "x.idx")
+    index.save(filename=p)
+    again = IndexL2Float.load_index(filename=p)
+    d2, l2 = again.search(queries=queries, ef_search=32, K=10)
+    np.testing.assert_array_equal(d2, d)
+    np.testing.assert_array_equal(l2, l)
+    d3, l3 = flatnav_b200.index.IndexL2Float.load_index(p).search(queries, 10, 32)
+    np.testing.assert_array_equal(d3, d)
+    np.testing.assert_array_equal(l3, l)
+    # re-ordering keeps the answers (labels travel with their nodes)
+    again.reorder(strategies=["rcm"])
+    with pytest.raises(ValueError, match="not a supported graph re-ordering strategy"):
+        again.reorder(strategies=["hilbert"])
+    d4, l4 = again.search(queries=queries, ef_search=32, K=10)
+    assert (l4 == l).mean() >= 0.999 and np.allclose(d4, d)
+    table = again.get_graph_outdegree_table()
+    assert len(table) == 30_000 and all(len(r) <= 32 for r in table[:100])
+
+
+def test_angular_uint8_and_labels():
+    rng = np.random.default_rng(1)
+    data = rng.integers(0, 255, size=(5000, 64), dtype=np.uint8)
+    ix = create(distance_type="angular", dim=64, dataset_size=5000, max_edges_per_node=16, index_data_type=DataType.uint8)
+    assert isinstance(ix, flatnav.index.IndexIPUint8)
+    labels = list(range(100, 5100))
+    ix.add(data=data, ef_construction=64, labels=labels)
+    with pytest.raises(ValueError, match="Incorrect number of labels"):
+        ix.add(data=data[:3], ef_construction=64, labels=[1, 2])
+    d, l = ix.search(queries=data[:50].astype(np.float64), K=5, ef_search=64)  # forcecast back to uint8
+    db, lb = ix.bruteforce(data[:50], 5)
+    assert (l[:, 0] == lb[:, 0]).mean() >= 0.9 and l.min() >= 100
+    with pytest.raises(RuntimeError):  # fewer than K reachable (bindings.cpp:184-189)
+        small = create(distance_type="l2", dim=4, dataset_size=8, max_edges_per_node=4)
+        small.add(data=np.eye(4, dtype=np.float32), ef_construction=8)
+        small.search(queries=np.zeros((1, 4), np.float32), K=6, ef_search=8)
