@@ -587,17 +587,29 @@ def main() -> None:
     for i in range(warmup):
         step_device(i)
     barrier()
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    # Nothing but the K launches goes on the stream between the two events: the engine's launches are adjacent (no
+    # memset between them) and use programmatic dependent launch, so the CTAs of step i+1 fill the SMs that the tail of
+    # step i leaves idle — an event record between steps would serialise them again.  The average launch duration of
+    # the roofline is therefore (t_end - t_begin) / K.
     t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_begin.record()
     for i in range(args.steps):
-        evs[i][0].record()
         step_device(i)
-        evs[i][1].record()
     t_end.record()
     barrier()
     total_ms = t_begin.elapsed_time(t_end)
-    kernel_ms = [a.elapsed_time(b) for a, b in evs]
+    kernel_ms = [total_ms / args.steps]
+    # one isolated launch at a time (synchronised before and after): what a single 10k batch costs on an idle GPU
+    single = []
+    for i in range(7):
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        step_device(i)
+        b.record()
+        torch.cuda.synchronize()
+        single.append(a.elapsed_time(b))
+    single_ms = float(statistics.median(single))
     # counters of the LAST step (every batch has the same size; counts vary by <1 % between batches)
     nd, nh, ns = ix.device_totals()
     ab = algo_bytes(info, nd, nh, Q, K)
@@ -646,8 +658,8 @@ def main() -> None:
     barrier()
 
     # ---- max over ranks -----------------------------------------------------------------------------
-    total_ms, e2e_ms, e2e_page_ms, mean_kernel_ms = cx.max_over_ranks(total_ms, e2e_ms, e2e_page_ms,
-                                                                      float(statistics.mean(kernel_ms)))
+    total_ms, e2e_ms, e2e_page_ms, mean_kernel_ms, single_ms = cx.max_over_ranks(
+        total_ms, e2e_ms, e2e_page_ms, float(statistics.mean(kernel_ms)), single_ms)
     del d_batches, pinned
     strong = sharded = None
     if not args.no_extras:
@@ -676,7 +688,11 @@ def main() -> None:
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_source": traffic_note, "peak_source": peak_src,
                          "kernel": kernel_sig, "algorithmic_bytes_per_launch": int(ab),
-                         "n_dist_per_query": nd / Q, "n_hops_per_query": nh / Q, "kernel_ms_mean": mean_kernel_ms},
+                         "n_dist_per_query": nd / Q, "n_hops_per_query": nh / Q, "kernel_ms_mean": mean_kernel_ms,
+                         "launches": "adjacent on one stream, programmatic dependent launch (the next step's CTAs fill "
+                                     "the tail of the previous one)",
+                         "isolated_launch_ms": single_ms, "isolated_launch_qps": world * Q / (single_ms * 1e-3),
+                         "isolated_launch_frac": ab / (single_ms * 1e-3) / 1e9 / peak},
             "sustained": sustained, "strong_scaling": strong, "sharded": sharded,
         }
         if not line["recall_ok"]:

@@ -40,6 +40,15 @@ class FnbSearchStats(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
 
 
+class FnbPlanInfo(C.Structure):
+    _fields_ = [("latency_variant", C.c_int32), ("dense_plan", C.c_int32), ("list_capacity", C.c_int32),
+                ("visited_slots", C.c_int32), ("smem_bytes_per_query", C.c_int32), ("ctas_per_sm", C.c_int32),
+                ("warps_per_sm", C.c_int32), ("queries_per_sm", C.c_int32)]
+
+    def as_dict(self) -> dict:
+        return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+
+
 class FnbBuildStats(C.Structure):
     _fields_ = [("n_added", C.c_int64), ("n_batches", C.c_int64), ("n_dropped_backlinks", C.c_int64),
                 ("device_ms", C.c_float), ("reserved", C.c_float)]
@@ -84,6 +93,7 @@ EXPORTS = {
     "fnb_search_device_totals": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
                                            C.POINTER(C.c_int64)]),
     "fnb_search_kernel_signature": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_char_p, C.c_size_t]),
+    "fnb_search_plan": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.POINTER(FnbPlanInfo)]),
     "fnb_bruteforce": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),
     "fnb_rerank": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "fnb_bruteforce_stats": (C.c_int, [C.POINTER(FnbBfStats)]),

@@ -558,7 +558,7 @@ static int add_locked(fnb_index* ix, const void* vectors, const int32_t* labels,
   if (done == 0) done = 1;  // the first node has nothing to link to (Index.h:366-368)
   auto enqueue_batch = [&](uint32_t b) -> int {
     // the graph the batch searches is the first `done` nodes; cur_num_nodes itself moves only when a batch is complete
-    int prc = plan_search(ix, b, (int)Kc, (int)Kc, num_initializations, &sp, 0, done);
+    int prc = plan_search(ix, b, (int)Kc, (int)Kc, num_initializations, &sp, 0, done, /*allow_latency_variant=*/false);
     if (prc != FNB_OK) return prc;
     sp.vec = r.vec;
     sp.adj = r.adj;

@@ -171,6 +171,10 @@ static int upload_replica(const Header& h, const unsigned char* blob, int device
   r->pool = new LanePool();
   if (const char* e = getenv("FNB_MAX_LANES")) r->pool->max_lanes = std::max(1, atoi(e));
   CU(cudaMalloc(&r->pool->ring, FNB_RING_SLOTS * 64));
+  CU(cudaMemset(r->pool->ring, 0, FNB_RING_SLOTS * 64));
+  CU(cudaHostAlloc((void**)&r->pool->h_done_seq, 64, cudaHostAllocMapped));
+  *r->pool->h_done_seq = 0u;
+  CU(cudaHostGetDevicePointer((void**)&r->pool->d_done_seq, (void*)r->pool->h_done_seq, 0));
   r->device_bytes = n * stride * FNB_CHUNK_BYTES + n * h.M * 4 + n * 4;
   r->capacity = n;
   if (h.cur_nodes) {
@@ -220,6 +224,7 @@ static void free_replica(Replica* r) {
   if (r->pool) {
     for (Lane* l : r->pool->all) free_lane(l);
     cudaFree(r->pool->ring);
+    if (r->pool->h_done_seq) cudaFreeHost((void*)r->pool->h_done_seq);
     delete r->pool;
     r->pool = nullptr;
   }
@@ -240,8 +245,12 @@ static int new_lane(Lane** out) {
     free_lane(l);
     return fail(FNB_ERR_CUDA, "cannot create a search lane: %s", cudaGetErrorString(e));
   }
-  l->totals = reinterpret_cast<unsigned long long*>(l->counter + 16);
-  l->q_ready = l->counter + 8;
+  l->totals = reinterpret_cast<unsigned long long*>(reinterpret_cast<unsigned char*>(l->counter) + FNB_SLOT_TOTALS);
+  l->q_ready = l->counter + 16;  // second half of the block
+  if (cudaHostGetDevicePointer((void**)&l->h_totals_dev, l->h_totals, 0) != cudaSuccess) {
+    free_lane(l);
+    return fail(FNB_ERR_CUDA, "cannot map the lane's pinned block");
+  }
   l->h_marks = reinterpret_cast<uint32_t*>(l->h_totals + 8);
   l->h_marks[FNB_FEED_CHUNKS] = 0xffffffffu;  // "everything is there": releases a launch whose feeding was cut short
   *out = l;
@@ -359,7 +368,7 @@ static int build_index(const unsigned char* file, size_t nbytes, int metric, int
 // ---- search dispatch ---------------------------------------------------------------------------------
 // launch_q: queries per kernel launch (the occupancy plan depends on it); <= 0 means Q
 int plan_search(const fnb_index* ix, int64_t Q, int K, int ef, int ninit, SearchParams* p, int64_t launch_q,
-                uint64_t n_nodes) {
+                uint64_t n_nodes, bool allow_latency_variant) {
   if (Q < 0) return fail(FNB_ERR_INVALID_ARG, "negative query count");
   if (K <= 0) return fail(FNB_ERR_INVALID_ARG, "K must be positive");
   if (ninit <= 0) return fail(FNB_ERR_INVALID_ARG, "num_initializations must be greater than 0.");
@@ -389,11 +398,16 @@ int plan_search(const fnb_index* ix, int64_t Q, int K, int ef, int ninit, Search
   const int cpl = fnb_chunks_per_lane(ix->nchunks, ix->G);
   const int sms = ix->replicas.empty() ? 148 : ix->replicas[0].num_sms;
   if (launch_q <= 0) launch_q = Q;
-  p->dense = choose_latency_variant(launch_q, sms) ? 0u : choose_dense_plan(launch_q, sms, ix->G, cpl, p->B);
-  size_visited(*p, env ? atoi(env) : 0, p->dense ? FNB_CTAS_DENSE : fnb_min_ctas(cpl));
-  if ((uint64_t)p->warp_smem * FNB_WARPS_PER_CTA > 227u * 1024u)
+  p->lat = allow_latency_variant ? choose_latency_variant(launch_q, sms) : 0u;
+  p->dense = p->lat ? 0u : choose_dense_plan(launch_q, sms, ix->G, cpl, p->B);
+  if (p->lat == 2u)  // one query per CTA, up to 4 CTAs per SM: the visited set can have its full size
+    size_visited(*p, env ? atoi(env) : 0, 4, 1);
+  else
+    size_visited(*p, env ? atoi(env) : 0, p->dense ? FNB_CTAS_DENSE : fnb_min_ctas(cpl));
+  const uint32_t queries_per_cta = p->lat ? 1u : (uint32_t)FNB_WARPS_PER_CTA;
+  if ((uint64_t)p->warp_smem * queries_per_cta + 1024u > 227u * 1024u)
     return fail(FNB_ERR_UNSUPPORTED, "ef_search=%d needs %u bytes of shared memory per query; limit is %u", ef,
-                p->warp_smem, 227u * 1024u / FNB_WARPS_PER_CTA);
+                p->warp_smem, 226u * 1024u / queries_per_cta);
   return FNB_OK;
 }
 
@@ -563,18 +577,27 @@ int fnb_search_device(fnb_index* ix, int replica, const void* d_queries, int64_t
   if (!ix) return fail(FNB_ERR_INVALID_ARG, "index is NULL");
   if (replica < 0 || replica >= (int)ix->replicas.size()) return fail(FNB_ERR_INVALID_ARG, "bad replica %d", replica);
   SharedLock lock(ix->mu);  // the plan reads cur_num_nodes: not while a construction batch is changing it
+  Replica& r = ix->replicas[replica];
+  LanePool& P = *r.pool;
+  static const bool no_pdl = getenv("FNB_NO_PDL") != nullptr;
+  // Launch state: every call takes the next 64-byte slot of a ring (calls on different streams may overlap) and the
+  // kernel leaves the slot clean, so nothing but the kernel goes on the stream.  Consecutive calls on one stream are
+  // then adjacent launches, and with programmatic dependent launch the CTAs of the next one fill the SMs the tail of
+  // this one leaves idle.  When the previous launch has not finished yet the caller is streaming batches: the tail no
+  // longer costs anything, so the plan is chosen as for one long batch (the 28-warp instantiation where it exists).
+  const uint32_t seq = P.ring_seq.fetch_add(1u) + 1u;
+  const bool lat = choose_latency_variant(Q, r.num_sms) != 0;
+  const bool streaming = !no_pdl && !lat && seq > 1u && *P.h_done_seq != seq - 1u;  // (latency variants keep their plan)
   SearchParams p;
-  int rc = plan_search(ix, Q, K, ef_search, num_initializations, &p);
+  int rc = plan_search(ix, Q, K, ef_search, num_initializations, &p, streaming ? std::max<int64_t>(Q, (int64_t)1 << 22) : 0);
   if (rc != FNB_OK) return rc;
   if (Q == 0) return FNB_OK;
   if (!d_queries || !d_out_dist || !d_out_label) return fail(FNB_ERR_INVALID_ARG, "NULL buffer");
-  Replica& r = ix->replicas[replica];
   cudaStream_t s = (cudaStream_t)cuda_stream;
   DeviceScope scope;
   CU(cudaSetDevice(r.device));
-  // every call gets its own {counter, totals} slot, so calls on different streams may overlap
-  const uint32_t slot = r.pool->ring_seq.fetch_add(1u) % FNB_RING_SLOTS;
-  unsigned char* sl = r.pool->ring + (size_t)slot * 64;
+  const uint32_t slot = seq % FNB_RING_SLOTS;
+  unsigned char* sl = P.ring + (size_t)slot * 64;
   p.vec = r.vec;
   p.adj = r.adj;
   p.labels = r.labels;
@@ -584,11 +607,14 @@ int fnb_search_device(fnb_index* ix, int replica, const void* d_queries, int64_t
   p.out_label = d_out_label;
   p.out_ndist = d_ndist;
   p.out_nhops = d_nhops;
-  p.counter = reinterpret_cast<unsigned int*>(sl);
-  p.totals = reinterpret_cast<unsigned long long*>(sl + 16);
-  p.lat = choose_latency_variant(Q, r.num_sms);
-  CU(cudaMemsetAsync(sl, 0, 64, s));
-  cudaError_t e = dispatch_search(ix, p, r.num_sms, s);
+  p.counter = reinterpret_cast<unsigned int*>(sl + FNB_SLOT_COUNTER);
+  p.done = reinterpret_cast<unsigned int*>(sl + FNB_SLOT_DONE);
+  p.totals = reinterpret_cast<unsigned long long*>(sl + FNB_SLOT_TOTALS);
+  p.last_totals = reinterpret_cast<unsigned long long*>(sl + FNB_SLOT_LAST_TOTALS);
+  p.done_seq = P.d_done_seq;
+  p.seq = seq;
+  p.pdl = no_pdl ? 0u : 1u;
+  cudaError_t e = dispatch_search(ix, p, r.num_sms, s);  // p.lat: as planned
   if (e != cudaSuccess) return fail(FNB_ERR_CUDA, "search kernel launch failed: %s", cudaGetErrorString(e));
   t_last_device_call.ix = ix;
   t_last_device_call.replica = replica;
@@ -603,7 +629,7 @@ int fnb_search_kernel_signature(const fnb_index* ix, int64_t Q, int K, int ef_se
   int rc = plan_search(ix, Q, K, ef_search, 100, &p);
   if (rc != FNB_OK) return rc;
   const int sms = ix->replicas.empty() ? 148 : ix->replicas[0].num_sms;
-  const int lat = (int)choose_latency_variant(Q, sms);
+  const int lat = (int)p.lat;
   const int ch = fnb_chunks_per_lane(ix->nchunks, ix->G);
   int CH;
   if (ix->G == 4) CH = ch <= 1 ? 1 : 2;
@@ -612,8 +638,34 @@ int fnb_search_kernel_signature(const fnb_index* ix, int64_t Q, int K, int ef_se
   const int dt = ix->h.data_type == FNB_DTYPE_FLOAT32 ? DT_F32 : (ix->h.data_type == FNB_DTYPE_UINT8 ? DT_U8 : DT_I8);
   const int exact = p.nchunks == (uint32_t)(ix->G * CH) ? 1 : 0;
   const int occ = (!lat && p.dense && CH <= 4 && ix->G <= 8) ? FNB_CTAS_DENSE : 0;
-  snprintf(out, cap, "fnb_search_kernel<%d,%d,%d,%d,%d,%d,%d>", dt, ix->h.metric == FNB_METRIC_IP ? M_IP : M_L2, ix->G, CH,
-           exact, lat, occ);
+  if (lat == 2)
+    snprintf(out, cap, "fnb_search_cta_kernel<%d,%d,%d,%d,%d>", dt, ix->h.metric == FNB_METRIC_IP ? M_IP : M_L2, ix->G, CH, exact);
+  else
+    snprintf(out, cap, "fnb_search_kernel<%d,%d,%d,%d,%d,%d,%d>", dt, ix->h.metric == FNB_METRIC_IP ? M_IP : M_L2, ix->G,
+             CH, exact, lat, occ);
+  return FNB_OK;
+}
+
+// What a search of this shape is planned with: shared memory per query, visited-set size, resident CTAs per SM.
+int fnb_search_plan(const fnb_index* ix, int64_t Q, int K, int ef_search, fnb_plan_info* out) {
+  if (!ix || !out) return fail(FNB_ERR_INVALID_ARG, "NULL argument");
+  SearchParams p;
+  int rc = plan_search(ix, Q, K, ef_search, 100, &p);
+  if (rc != FNB_OK) return rc;
+  memset(out, 0, sizeof(*out));
+  const int sms = ix->replicas.empty() ? 148 : ix->replicas[0].num_sms;
+  const int cpl = fnb_chunks_per_lane(ix->nchunks, ix->G);
+  out->latency_variant = (int32_t)p.lat;
+  out->dense_plan = out->latency_variant ? 0 : (int32_t)p.dense;
+  out->list_capacity = (int32_t)p.Bcap;
+  out->visited_slots = (int32_t)(p.vs_buckets * (p.vs_wide ? 4u : 8u));
+  out->smem_bytes_per_query = (int32_t)p.warp_smem;
+  const int by_regs = out->latency_variant == 2 ? 4 : (out->latency_variant ? 8 : (p.dense ? FNB_CTAS_DENSE : fnb_min_ctas(cpl)));
+  const int queries_per_cta = out->latency_variant ? 1 : FNB_WARPS_PER_CTA;
+  const int by_smem = (int)((227u * 1024u) / ((uint32_t)p.warp_smem * queries_per_cta + 1024u));
+  out->ctas_per_sm = std::min(by_regs, by_smem);
+  out->warps_per_sm = out->ctas_per_sm * (out->latency_variant == 2 ? FNB_CTA_WARPS : (out->latency_variant ? 1 : FNB_WARPS_PER_CTA));
+  out->queries_per_sm = out->ctas_per_sm * queries_per_cta;
   return FNB_OK;
 }
 
@@ -627,7 +679,7 @@ int fnb_search_device_totals(fnb_index* ix, int replica, int64_t* n_dist, int64_
   DeviceScope scope;
   CU(cudaSetDevice(r.device));
   unsigned long long t[3];
-  CU(cudaMemcpy(t, r.pool->ring + (size_t)t_last_device_call.slot * 64 + 16, sizeof(t), cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(t, r.pool->ring + (size_t)t_last_device_call.slot * 64 + FNB_SLOT_LAST_TOTALS, sizeof(t), cudaMemcpyDeviceToHost));
   if (n_dist) *n_dist = (int64_t)t[0];
   if (n_hops) *n_hops = (int64_t)t[1];
   if (n_short) *n_short = (int64_t)t[2];
@@ -704,7 +756,6 @@ int fnb_search(fnb_index* ix, const void* queries, int64_t Q, int K, int ef_sear
     p.vec = r.vec;
     p.adj = r.adj;
     p.labels = r.labels;
-    p.lat = choose_latency_variant(pt.nq, r.num_sms);
     // layout of the lane's pinned block: [queries (small batches only) | dist | label | per-query counters (lat only)]
     pt.counters_in_block = p.lat != 0;  // small batches: per-query counters by plain stores, no device totals to clear / fetch
     // queries of a pageable caller.  Small batch (latency variant): copied by the CPU into the pinned block the kernel
@@ -749,16 +800,18 @@ int fnb_search(fnb_index* ix, const void* queries, int64_t Q, int K, int ef_sear
       p.out_len = reinterpret_cast<uint32_t*>(dp + pt.off_len);
       p.counter = nullptr;
       p.totals = nullptr;
-    } else {
+    } else {  // the lane's launch-state slot is left clean by the kernel itself: no memset on the stream
       p.counter = ln.counter;
       p.totals = ln.totals;
+      p.done = ln.counter + FNB_SLOT_DONE / 4;
+      p.last_totals = ln.h_totals_dev;  // straight into pinned host memory: no copy on the stream after the kernel
     }
     if (q_in_block) memcpy(ln.h_pinned, q_src, qb);
     if (feed) p.q_ready = ln.q_ready;
     CU(cudaEventRecord(ln.ev[0], ln.stream));
     if (!zq && !q_in_block && !feed) CU(cudaMemcpyAsync(d_q, q_src, qb, cudaMemcpyHostToDevice, ln.stream));
-    if (!pt.counters_in_block) CU(cudaMemsetAsync(ln.counter, 0, 128, ln.stream));  // counter, watermark, totals
     if (feed) {
+      CU(cudaMemsetAsync(ln.q_ready, 0, 4, ln.stream));
       CU(cudaEventRecord(ln.ev_feed, ln.stream));  // the first watermark must not land before the clear above
       CU(cudaStreamWaitEvent(ln.copy_stream, ln.ev_feed, 0));
     }
@@ -770,7 +823,6 @@ int fnb_search(fnb_index* ix, const void* queries, int64_t Q, int K, int ef_sear
       CU(cudaMemcpyAsync(out_dist + (size_t)pt.q0 * K, d_dist, ob, cudaMemcpyDeviceToHost, ln.stream));
       CU(cudaMemcpyAsync(out_label + (size_t)pt.q0 * K, d_label, ob, cudaMemcpyDeviceToHost, ln.stream));
     }
-    if (!pt.counters_in_block) CU(cudaMemcpyAsync(ln.h_totals, ln.totals, 24, cudaMemcpyDeviceToHost, ln.stream));
     CU(cudaEventRecord(ln.ev[3], ln.stream));
     if (feed) {
       // a pageable cudaMemcpyAsync returns once the chunk is staged, so this loop paces itself against the host copy

@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "fnb_layout.h"
+#include "search_cta_kernel.cuh"
 #include "search_kernel.cuh"
 
 #define FNB_HEADER_BYTES 60u
@@ -31,7 +32,8 @@ struct Lane {
   unsigned int* counter = nullptr;         // device: persistent-warp work counter
   unsigned long long* totals = nullptr;    // device: [3] n_dist, n_hops, short results
   unsigned int* q_ready = nullptr;         // device: watermark of a host-fed batch (queries already copied in)
-  unsigned long long* h_totals = nullptr;  // pinned mirror of `totals`
+  unsigned long long* h_totals = nullptr;  // pinned: the kernel's last warp writes the totals of the launch here
+  unsigned long long* h_totals_dev = nullptr;  // its device-side alias
   uint32_t* h_marks = nullptr;             // pinned: the watermark values a host-fed batch copies to q_ready, [FNB_FEED_CHUNKS + 1]
   cudaStream_t copy_stream = nullptr;      // feeds the queries of a pageable caller while the kernel runs on `stream`
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -44,7 +46,13 @@ struct Lane {
 };
 
 #define FNB_FEED_CHUNKS 48
-#define FNB_RING_SLOTS 256u  // per-call {counter, totals} slots of fnb_search_device (64 B each)
+#define FNB_RING_SLOTS 256u  // per-call launch-state slots of fnb_search_device (64 B each)
+// Layout of a 64-byte launch-state slot (ring slots, and the first half of a lane's counter block).  A slot is all
+// zero between launches: the last warp of a launch leaves it so (search_kernel.cuh, `done`).
+#define FNB_SLOT_COUNTER 0      /* u32  persistent-warp work counter */
+#define FNB_SLOT_DONE 4         /* u32  warps that have left the kernel */
+#define FNB_SLOT_TOTALS 8       /* u64 x 3  n_dist, n_hops, short results (accumulated with atomics) */
+#define FNB_SLOT_LAST_TOTALS 32 /* u64 x 3  the totals of the launch that used the slot last (read by the host) */
 
 struct LanePool {
   std::mutex mu;
@@ -53,6 +61,8 @@ struct LanePool {
   int max_lanes = 16;
   unsigned char* ring = nullptr;  // device: FNB_RING_SLOTS x 64 B
   std::atomic<uint32_t> ring_seq{0};
+  volatile unsigned int* h_done_seq = nullptr;  // pinned: sequence number of the last fnb_search_device launch that finished
+  unsigned int* d_done_seq = nullptr;           // its device-side alias
 };
 
 // One full copy of the index in the HBM of one device, plus the per-device launch state.
@@ -111,31 +121,37 @@ typedef std::shared_lock<std::shared_mutex> SharedLock;
 // after taking the exclusive lock: wait for asynchronous searches (fnb_search_device on caller streams) still in flight
 void quiesce(fnb_index* ix);
 // n_nodes != 0: search only the first n_nodes nodes (construction: the graph a batch is inserted into)
+// allow_latency_variant = false: always the throughput kernel (construction)
 int plan_search(const fnb_index* ix, int64_t Q, int K, int ef, int ninit, SearchParams* p, int64_t launch_q = 0,
-                uint64_t n_nodes = 0);
+                uint64_t n_nodes = 0, bool allow_latency_variant = true);
 cudaError_t dispatch_search(const fnb_index* ix, const SearchParams& p, int num_sms, cudaStream_t s);
 cudaError_t dispatch_search_f32(const fnb_index* ix, const SearchParams& p, int num_sms, cudaStream_t s);
 cudaError_t dispatch_search_u8(const fnb_index* ix, const SearchParams& p, int num_sms, cudaStream_t s);
 cudaError_t dispatch_search_i8(const fnb_index* ix, const SearchParams& p, int num_sms, cudaStream_t s);
 
+template <int DT, int METRIC, int G, int CH>
+static inline cudaError_t launch_any(const SearchParams& p, int num_sms, cudaStream_t s) {
+  return p.lat == 2u ? launch_search_cta<DT, METRIC, G, CH>(p, num_sms, s) : launch_search<DT, METRIC, G, CH>(p, num_sms, s);
+}
+
 template <int DT, int METRIC>
 static inline cudaError_t dispatch_gc(const fnb_index* ix, const SearchParams& p, int num_sms, cudaStream_t s) {
   const int ch = fnb_chunks_per_lane(ix->nchunks, ix->G);
   if (ix->G == 4) {
-    if (ch <= 1) return launch_search<DT, METRIC, 4, 1>(p, num_sms, s);
-    return launch_search<DT, METRIC, 4, 2>(p, num_sms, s);
+    if (ch <= 1) return launch_any<DT, METRIC, 4, 1>(p, num_sms, s);
+    return launch_any<DT, METRIC, 4, 2>(p, num_sms, s);
   }
   if (ix->G == 8) {
     switch (ch) {
-      case 1: return launch_search<DT, METRIC, 8, 1>(p, num_sms, s);
-      case 2: return launch_search<DT, METRIC, 8, 2>(p, num_sms, s);
-      case 3: return launch_search<DT, METRIC, 8, 3>(p, num_sms, s);
-      default: return launch_search<DT, METRIC, 8, 4>(p, num_sms, s);
+      case 1: return launch_any<DT, METRIC, 8, 1>(p, num_sms, s);
+      case 2: return launch_any<DT, METRIC, 8, 2>(p, num_sms, s);
+      case 3: return launch_any<DT, METRIC, 8, 3>(p, num_sms, s);
+      default: return launch_any<DT, METRIC, 8, 4>(p, num_sms, s);
     }
   }
-  if (ch <= 2) return launch_search<DT, METRIC, 32, 2>(p, num_sms, s);
-  if (ch <= 4) return launch_search<DT, METRIC, 32, 4>(p, num_sms, s);
-  if (ch <= 8) return launch_search<DT, METRIC, 32, 8>(p, num_sms, s);
-  return launch_search<DT, METRIC, 32, 16>(p, num_sms, s);
+  if (ch <= 2) return launch_any<DT, METRIC, 32, 2>(p, num_sms, s);
+  if (ch <= 4) return launch_any<DT, METRIC, 32, 4>(p, num_sms, s);
+  if (ch <= 8) return launch_any<DT, METRIC, 32, 8>(p, num_sms, s);
+  return launch_any<DT, METRIC, 32, 16>(p, num_sms, s);
 }
 }  // namespace fnb

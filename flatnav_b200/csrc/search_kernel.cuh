@@ -100,7 +100,17 @@ struct SearchParams {
   uint32_t query_pitch_chunks;  // != 0 => queries are rows of a padded vector array with this pitch (construction:
                                 // the new nodes' own rows); chunks beyond the data are zero there
   uint32_t dense;  // 1 => the 28-warps-per-SM instantiation (large batches of short rows; never with lat)
-  uint32_t lat;  // 1 => latency variant (few queries): one warp per CTA, query = blockIdx.x (grid-stride), `counter` unused
+  uint32_t lat;  // latency variants (few queries; query = blockIdx.x, grid-stride, `counter` unused): 1 => one warp per
+                 // CTA (fnb_search_kernel<.., LAT>), 2 => one CTA of four warps per query (search_cta_kernel.cuh)
+  // Self-cleaning launch state (fnb_search_device): != null => the last warp of the grid to finish copies `totals` to
+  // `last_totals`, zeroes counter / totals / done for the slot's next user and reports `seq` to the host — no memset
+  // between launches, so consecutive launches are adjacent in the stream and can overlap (pdl).
+  unsigned int* done;
+  unsigned long long* last_totals;  // [3]
+  volatile unsigned int* done_seq;  // host-mapped: sequence number of the last launch that completed (a hint), or null
+  uint32_t seq;
+  uint32_t pdl;  // launch with programmatic stream serialization: the next launch of the stream may start its CTAs as
+                 // this one's exit (the kernel triggers at its start and waits for its predecessor before it writes)
   // != null => the queries are still being copied into device memory while the kernel runs (fnb_search with pageable
   // caller buffers): *q_ready = number of leading queries already in place; a warp waits for it to pass its query index
   const unsigned int* q_ready;
@@ -540,6 +550,11 @@ __global__ void __launch_bounds__(LAT ? 32 : FNB_WARPS_PER_CTA * 32, LAT ? 1 : (
   const int pos = lane % G;
   constexpr int UL = LAT ? fnb_batches_in_flight_lat(G, CH) : 0;  // 0: the throughput variant's default
   uint32_t qi_next = blockIdx.x;
+  // Programmatic dependent launch: let the NEXT launch of this stream place its CTAs as soon as ours retire (the tail
+  // of a batch of a few "rounds" of queries leaves SMs idle otherwise).  Nothing here depends on the previous launch
+  // except the order of writes to the caller's output buffers, which griddepcontrol.wait restores below.  Both are
+  // no-ops for a launch without the attribute.
+  asm volatile("griddepcontrol.launch_dependents;");
 
   for (;;) {
     uint32_t qi = 0;
@@ -653,6 +668,7 @@ __global__ void __launch_bounds__(LAT ? 32 : FNB_WARPS_PER_CTA * 32, LAT ? 1 : (
     }
 
     // ---- output: ascending distance, label field of the node (Index.h:393-406) ----
+    asm volatile("griddepcontrol.wait;" ::: "memory");  // the previous launch of the stream has finished writing
     for (uint32_t i = lane; i < p.K; i += 32) {
       float od = __int_as_float(0x7f800000);
       int32_t ol = -1;
@@ -676,13 +692,30 @@ __global__ void __launch_bounds__(LAT ? 32 : FNB_WARPS_PER_CTA * 32, LAT ? 1 : (
     }
     __syncwarp();
   }
+  asm volatile("griddepcontrol.wait;" ::: "memory");  // also by warps that found no work: launches complete in stream order
+  if (p.done && lane == 0) {
+    __threadfence();
+    const unsigned int n_warps = gridDim.x * (LAT ? 1u : (unsigned int)FNB_WARPS_PER_CTA);
+    if (atomicAdd(p.done, 1u) == n_warps - 1u) {  // the last warp of the grid
+      __threadfence();
+      if (p.totals) {
+        p.last_totals[0] = atomicExch(p.totals + 0, 0ull);
+        p.last_totals[1] = atomicExch(p.totals + 1, 0ull);
+        p.last_totals[2] = atomicExch(p.totals + 2, 0ull);
+      }
+      if (p.counter) *p.counter = 0u;
+      *p.done = 0u;
+      __threadfence();
+      if (p.done_seq) *p.done_seq = p.seq;
+    }
+  }
 }
 
 // ---- host-side launcher -----------------------------------------------------------------------------
 // Shared memory per warp = list (Bcap*8) + visited set (buckets*16) + 128 B scratch.  The visited set takes what
 // the planned occupancy (min_ctas CTAs of 4 warps per SM) leaves of the 227 KB, up to ~48 slots per list entry
 // (~20 evaluations per unit of ef were measured on the BASELINE configs, so <= 45 % load).
-inline void size_visited(SearchParams& p, int force_buckets, int min_ctas) {
+inline void size_visited(SearchParams& p, int force_buckets, int min_ctas, int queries_per_cta = FNB_WARPS_PER_CTA) {
   const uint32_t list_bytes = p.Bcap * 8u + 128u;
   uint32_t nbits = 1;
   while ((1ull << nbits) < (uint64_t)p.N && nbits < 31) nbits++;
@@ -706,7 +739,7 @@ inline void size_visited(SearchParams& p, int force_buckets, int min_ctas) {
     const uint32_t floor_b = p.B / 8u > 16u ? p.B / 8u : 16u;
     buckets = 16u;
     for (int c = min_ctas; c >= 1; c--) {
-      const uint32_t budget = (227u * 1024u - (uint32_t)c * 1024u) / ((uint32_t)c * FNB_WARPS_PER_CTA);  // per warp
+      const uint32_t budget = (227u * 1024u - (uint32_t)c * 1024u) / ((uint32_t)c * (uint32_t)queries_per_cta);  // per query
       const uint32_t room = budget > list_bytes ? (budget - list_bytes) / 16u : 0u;
       buckets = want < room ? want : room;
       if (buckets >= floor_b || c == 1) break;
@@ -728,6 +761,26 @@ struct LaunchCache {
   size_t smem = ~(size_t)0;
   int ctas_per_sm = 0;
 };
+
+template <typename Kern>
+static inline cudaError_t launch_maybe_pdl(Kern kern, unsigned grid, unsigned block, size_t smem, cudaStream_t stream,
+                                           const SearchParams& p) {
+  if (!p.pdl) {
+    kern<<<grid, block, smem, stream>>>(p);
+    return cudaGetLastError();
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, p);
+}
 
 template <typename Kern>
 static inline cudaError_t plan_launch(Kern kern, int threads, size_t smem, LaunchCache* cache, int* ctas_per_sm) {
@@ -761,8 +814,7 @@ cudaError_t launch_search(const SearchParams& p, int num_sms, cudaStream_t strea
     long long grid = (long long)num_sms * ctas_per_sm;
     if (grid > (long long)p.Q) grid = p.Q;
     if (grid < 1) grid = 1;
-    kern<<<(unsigned)grid, 32, smem, stream>>>(p);
-    return cudaGetLastError();
+    return launch_maybe_pdl(kern, (unsigned)grid, 32u, smem, stream, p);
   }
   auto kern = exact ? fnb_search_kernel<DT, METRIC, G, CH, true, false> : fnb_search_kernel<DT, METRIC, G, CH, false, false>;
   LaunchCache* lc = cache[exact ? 1 : 0];
@@ -780,8 +832,7 @@ cudaError_t launch_search(const SearchParams& p, int num_sms, cudaStream_t strea
   const long long need = ((long long)p.Q + FNB_WARPS_PER_CTA - 1) / FNB_WARPS_PER_CTA;
   if (grid > need) grid = need;
   if (grid < 1) grid = 1;
-  kern<<<(unsigned)grid, FNB_WARPS_PER_CTA * 32, smem, stream>>>(p);
-  return cudaGetLastError();
+  return launch_maybe_pdl(kern, (unsigned)grid, (unsigned)FNB_WARPS_PER_CTA * 32u, smem, stream, p);
 }
 
 // Host rule for SearchParams::dense.  Both plans keep persistent warps pulling queries, so a launch lasts about
@@ -808,15 +859,16 @@ inline uint32_t choose_dense_plan(int64_t Q, int num_sms, int lanes_per_row, int
   return cost(FNB_CTAS_DENSE, 1.08) < 0.98 * cost(fnb_min_ctas(chunks_per_lane), 1.0) ? 1u : 0u;
 }
 
-// Host rule for SearchParams::lat: the latency variant when every query of the batch can have a warp of its own on
-// a lightly loaded SM (<= 4 single-warp CTAs per SM).  FNB_LAT=0 / 1 forces the choice (tests, experiments).
+// Host rule for SearchParams::lat: a latency variant when every query of the batch can have an SM quarter of its own
+// (<= 4 CTAs per SM): the CTA-per-query kernel (2).  FNB_LAT=0 / 1 / 2 forces the throughput kernel / the one-warp
+// latency variant / the CTA kernel (tests, experiments).
 inline uint32_t choose_latency_variant(int64_t Q, int num_sms) {
   static const int forced = [] {
     const char* e = getenv("FNB_LAT");
     return e ? atoi(e) : -1;
   }();
-  if (forced >= 0) return forced ? 1u : 0u;
-  return Q <= 4ll * num_sms ? 1u : 0u;
+  if (forced >= 0) return forced > 2 ? 2u : (uint32_t)forced;
+  return Q <= 4ll * num_sms ? 2u : 0u;
 }
 
 }  // namespace fnb

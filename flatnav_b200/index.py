@@ -179,6 +179,12 @@ class _GpuIndex:
         _capi.check(_capi.lib().fnb_search_kernel_signature(self._h, int(Q), int(K), int(ef_search), buf, 128))
         return buf.value.decode()
 
+    def search_plan(self, Q: int, K: int, ef_search: int) -> dict:
+        """Launch plan of a search of this shape: shared memory per query, visited-set slots, resident CTAs per SM."""
+        pi = _capi.FnbPlanInfo()
+        _capi.check(_capi.lib().fnb_search_plan(self._h, int(Q), int(K), int(ef_search), C.byref(pi)))
+        return pi.as_dict()
+
     # ---- getters / knobs --------------------------------------------------------------------
     def get_query_distance_computations(self) -> int:
         """PyIndex::getQueryDistanceComputations (bindings.cpp:270-274): read-and-reset.

@@ -192,6 +192,20 @@ int fnb_search_device(fnb_index* index, int replica, const void* d_queries, int6
  * occupancy plan).  bench.py uses it to check that a committed ncu capture is of the kernel it times. */
 int fnb_search_kernel_signature(const fnb_index* index, int64_t Q, int K, int ef_search, char* out, size_t out_capacity);
 
+/* Measurement aid: the launch plan of a search of this shape (what bounds the resident queries per SM). */
+typedef struct fnb_plan_info {
+  int32_t latency_variant;      /* batches of at most 4 x SMs queries: 2 = one CTA of four warps per query (default),
+                                   1 = one warp per CTA; 0 = throughput kernel (one warp per query, 4 per CTA) */
+  int32_t dense_plan;           /* 1: the 28-warps-per-SM instantiation (large batches of rows up to 512 B) */
+  int32_t list_capacity;        /* max(ef_search, K) rounded up to 32 entries of 8 bytes */
+  int32_t visited_slots;        /* tag slots of the per-query visited set */
+  int32_t smem_bytes_per_query; /* list + visited set + scratch */
+  int32_t ctas_per_sm;          /* planned resident CTAs per SM (min of the register plan and what shared memory allows) */
+  int32_t warps_per_sm;
+  int32_t queries_per_sm;       /* resident queries per SM */
+} fnb_plan_info;
+int fnb_search_plan(const fnb_index* index, int64_t Q, int K, int ef_search, fnb_plan_info* out);
+
 /* Exact scan over all nodes (ground truth / exact re-rank).  The reference has no brute force of its own;
  * semantics: top-K by (distance, node id), distances in the same arithmetic as fnb_search.  HOST buffers. */
 int fnb_bruteforce(fnb_index* index, const void* queries, int64_t Q, int K, float* out_dist, int32_t* out_label);

@@ -10,6 +10,7 @@ import pytest
 import flatnav
 import flatnav_b200
 from flatnav.data_type import DataType
+from flatnav_b200 import synthetic
 from flatnav.index import IndexIPFloat, IndexL2Float, create
 
 pytestmark = pytest.mark.gpu
@@ -29,12 +30,13 @@ def compute_recall(index, queries, ground_truth, ef_search, k=100):  # test_util
     return float(np.mean([sum(1 for n in row if n in gts[i]) / k for i, row in enumerate(top_k_indices)]))
 
 
-def test_l2_index_random_dataset_like_the_reference_unit_test(tmp_path, capsys):
-    rng = np.random.default_rng(0)
-    training_set = rng.random((30_000, 784))  # float64, like np.random.rand
-    queries = rng.random((500, 784))
+def test_l2_index_random_dataset_like_the_reference_unit_test(tmp_path, capfd):
+    # float64 arrays like the reference test's np.random.rand ones (the binding casts them), but drawn from the latent
+    # generator: on uniform random 784-dimensional points recall@100 is below 0.5 at any sane ef_search
+    training_set = synthetic.make("latent", 30_000, 784).astype(np.float64)
+    queries = synthetic.make("latent", 500, 784, queries=True).astype(np.float64)
     index = create_index(distance_type="l2", dim=784, dataset_size=len(training_set), max_edges_per_node=32)
-    assert "max_edges_per_node (M): 32" in capsys.readouterr().out  # verbose=True prints the summary
+    assert "max_edges_per_node (M): 32" in capfd.readouterr().out  # verbose=True prints the summary (from C++)
     assert hasattr(index, "max_edges_per_node") and index.max_edges_per_node == 32
     index.set_num_threads(os.cpu_count())  # test_parallel_insertions.py:30
     assert index.num_threads == os.cpu_count()
@@ -43,7 +45,7 @@ def test_l2_index_random_dataset_like_the_reference_unit_test(tmp_path, capsys):
     index.add(data=training_set, ef_construction=64)
     # the reference's test only checks that search runs on random ground truth; here recall is checked for real
     _, gt = index.bruteforce(queries, 100)
-    assert compute_recall(index=index, queries=queries, ground_truth=gt, ef_search=200) >= 0.85
+    assert compute_recall(index=index, queries=queries, ground_truth=gt, ef_search=200) >= 0.9
     d, l = index.search(queries=queries, ef_search=32, K=10)
     assert d.dtype == np.float32 and l.dtype == np.int32 and d.shape == (500, 10) and d.flags.owndata is not None
     d1, l1 = index.search_single(query=queries[3], ef_search=32, K=10)
@@ -68,15 +70,17 @@ def test_l2_index_random_dataset_like_the_reference_unit_test(tmp_path, capsys):
     again.reorder(strategies=["rcm"])
     with pytest.raises(ValueError, match="not a supported graph re-ordering strategy"):
         again.reorder(strategies=["hilbert"])
+    # (the entry probes go by node id, Index.h:851-868, so a re-ordered graph starts elsewhere: same quality, not same bytes)
+    _, gt10 = again.bruteforce(queries, 10)
     d4, l4 = again.search(queries=queries, ef_search=32, K=10)
-    assert (l4 == l).mean() >= 0.999 and np.allclose(d4, d)
+    rec = lambda ll: np.mean([len(set(a) & set(b)) / 10 for a, b in zip(ll.tolist(), gt10.tolist())])
+    assert abs(rec(l4) - rec(l)) <= 0.02 and np.all(np.diff(d4, axis=1) >= 0)
     table = again.get_graph_outdegree_table()
     assert len(table) == 30_000 and all(len(r) <= 32 for r in table[:100])
 
 
 def test_angular_uint8_and_labels():
-    rng = np.random.default_rng(1)
-    data = rng.integers(0, 255, size=(5000, 64), dtype=np.uint8)
+    data = synthetic.make("latent-u8", 5000, 64)
     ix = create(distance_type="angular", dim=64, dataset_size=5000, max_edges_per_node=16, index_data_type=DataType.uint8)
     assert isinstance(ix, flatnav.index.IndexIPUint8)
     labels = list(range(100, 5100))
@@ -85,7 +89,7 @@ def test_angular_uint8_and_labels():
         ix.add(data=data[:3], ef_construction=64, labels=[1, 2])
     d, l = ix.search(queries=data[:50].astype(np.float64), K=5, ef_search=64)  # forcecast back to uint8
     db, lb = ix.bruteforce(data[:50], 5)
-    assert (l[:, 0] == lb[:, 0]).mean() >= 0.9 and l.min() >= 100
+    assert np.mean([len(set(a) & set(b)) / 5 for a, b in zip(l.tolist(), lb.tolist())]) >= 0.8 and l.min() >= 100
     with pytest.raises(RuntimeError):  # fewer than K reachable (bindings.cpp:184-189)
         small = create(distance_type="l2", dim=4, dataset_size=8, max_edges_per_node=4)
         small.add(data=np.eye(4, dtype=np.float32), ef_construction=8)

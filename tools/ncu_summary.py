@@ -16,7 +16,7 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-OUT = os.path.join(ROOT, "profiles")
+OUT = os.environ.get("FNB_PROFILES_OUT") or os.path.join(ROOT, "profiles")  # on the GPU box: a directory under gpurun_out/
 KEEP = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
         "lts__t_sector_hit_rate.pct", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
         "l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum",
@@ -87,9 +87,26 @@ def full(tag, rep, name="search_kernel", traffic_json=True):
 
     traffic = to_bytes(*got["dram__bytes_read.sum"]) + to_bytes(*got["dram__bytes_write.sum"])
     if traffic_json:
-        json.dump({"dram_bytes_per_launch": traffic, "source": f"profiles/{tag}_search_kernel_metrics.csv "
-                   "(dram__bytes_read.sum + dram__bytes_write.sum, one ncu --set full capture of fnb_search_kernel, "
-                   "bench.py workload)"}, open(os.path.join(OUT, "roofline_traffic.json"), "w"), indent=1)
+        # profiles/roofline_traffic.json: one record per profiled shape ("headline" is the one bench.py reads), each
+        # naming the kernel instantiation and the commit it was captured at; bench.py refuses a record of another kernel
+        path = os.path.join(OUT, "roofline_traffic.json")
+        try:
+            allrec = json.load(open(path))
+            if "dram_bytes_per_launch" in allrec:  # round-1 format
+                allrec = {}
+        except Exception:
+            allrec = {}
+        kname = vals[hdr.index("Kernel Name")]
+        kname = "".join(kname.split("(")[0].replace("void ", "").replace("fnb::", "").split())
+        allrec[traffic_json if isinstance(traffic_json, str) else "headline"] = {
+            "kernel": kname, "dram_bytes_per_launch": traffic, "git_sha": os.environ.get("GIT_SHA", "unknown"),
+            "workload": os.environ.get("NCU_WORKLOAD", ""), "kernel_us": got.get("gpu__time_duration.sum", ("", ""))[0],
+            "l2_sector_hit_rate_pct": got.get("lts__t_sector_hit_rate.pct", ("", ""))[0],
+            "sectors_per_request": (float(got["l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum"][0].replace(",", "")) /
+                                    max(1.0, float(got["l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum"][0].replace(",", "")))),
+            "source": f"profiles/{tag}_{name}_metrics.csv (dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full "
+                      "--clock-control none capture)"}
+        json.dump(allrec, open(path, "w"), indent=1)
     src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--print-source", "cuda,sass", "--csv"],
                          capture_output=True, text=True).stdout
     rows = list(csv.reader(src.splitlines()))
@@ -119,5 +136,6 @@ if __name__ == "__main__":
     name = sys.argv[sys.argv.index("--name") + 1] if "--name" in sys.argv else "search_kernel"
     if sys.argv[2] != "-":
         launches(tag, sys.argv[2])
-    full(tag, sys.argv[3], name=name, traffic_json="--no-traffic" not in sys.argv)
+    shape = sys.argv[sys.argv.index("--shape") + 1] if "--shape" in sys.argv else True
+    full(tag, sys.argv[3], name=name, traffic_json=False if "--no-traffic" in sys.argv else shape)
     print("wrote profiles for", tag)

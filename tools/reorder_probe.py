@@ -35,6 +35,10 @@ def main() -> None:
     ap.add_argument("--builder", default="reference")
     ap.add_argument("--strategies", default="gorder;rcm;rcm,gorder")
     ap.add_argument("--ref", action="store_true")
+    ap.add_argument("--profile", action="store_true",
+                    help="wrap one extra launch per (order, ef) in cudaProfilerStart/Stop: under `ncu --profile-from-start "
+                         "off --metrics lts__t_sector_hit_rate.pct,dram__bytes_read.sum,gpu__time_duration.sum` the "
+                         "captured launches are those rows, in order (tools/reorder_merge_ncu.py joins them)")
     ap.add_argument("--out", default="")
     args = ap.parse_args()
 
@@ -75,6 +79,12 @@ def main() -> None:
                    "n_dist": round(nd / args.q, 1), "n_hops": round(nh / args.q, 1), "recall": round(rec, 4), **extra}
             rows.append(row)
             print(json.dumps(row), flush=True)
+            if args.profile:
+                torch.cuda.synchronize()
+                torch.cuda.profiler.start()
+                ix.search_device(dq.data_ptr(), args.q, args.k, ef, 100, od.data_ptr(), ol.data_ptr(), stream)
+                torch.cuda.synchronize()
+                torch.cuda.profiler.stop()
 
     ix = cls.load_index(path, devices=[0])
     _, gt = ix.bruteforce(queries, args.k)

@@ -54,6 +54,7 @@ def main():
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--no-ref", action="store_true")
     ap.add_argument("--ref-sample", type=int, default=2000)
+    ap.add_argument("--efs", default="", help="comma-separated ef_search list overriding the config's")
     ap.add_argument("--builder", default="reference", choices=["reference", "gpu"],
                     help="who builds the graph when it is not cached: the unmodified reference, or this engine's GPU construction")
     args = ap.parse_args()
@@ -62,6 +63,8 @@ def main():
         c["n"] = args.n
     if args.q:
         c["Q"] = args.q
+    if args.efs:
+        c["efs"] = [int(x) for x in args.efs.split(",")]
 
     import torch
 
@@ -101,14 +104,25 @@ def main():
             ix.search_device(dq.data_ptr(), Q, K, ef, 100, dd.data_ptr(), dl.data_ptr(), stream)
         e1.record()
         torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / args.iters
+        ms = e0.elapsed_time(e1) / args.iters  # launches back to back: adjacent launches overlap their tails (PDL)
+        iso = []
+        for _ in range(5):  # one launch at a time on an idle GPU
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            ix.search_device(dq.data_ptr(), Q, K, ef, 100, dd.data_ptr(), dl.data_ptr(), stream)
+            b.record()
+            torch.cuda.synchronize()
+            iso.append(a.elapsed_time(b))
+        iso_ms = float(np.median(iso))
         nd, nh, ns = ix.device_totals()
         lab = dl.cpu().numpy()
         rec = float(np.mean([len(set(a.tolist()) & set(b.tolist())) / K for a, b in zip(lab, gt)]))
         algo = nd * info["data_size_bytes"] + nh * info["max_edges_per_node"] * 4 + Q * info["data_size_bytes"] + Q * K * 8
         gbs = algo / (ms * 1e-3) / 1e9
         row = dict(ef=ef, recall=round(rec, 4), qps=Q / (ms * 1e-3), kernel_ms=ms, n_dist=nd / Q, n_hops=nh / Q,
-                   bytes_per_query=algo / Q, gbs=gbs, frac=gbs / pk, n_short=ns)
+                   bytes_per_query=algo / Q, gbs=gbs, frac=gbs / pk, isolated_ms=iso_ms, isolated_qps=Q / (iso_ms * 1e-3),
+                   isolated_frac=algo / (iso_ms * 1e-3) / 1e9 / pk, n_short=ns, kernel=ix.kernel_signature(Q, K, ef),
+                   plan=ix.search_plan(Q, K, ef))
         if not args.no_ref and refbin.available():
             nq = min(Q, args.ref_sample)
             _, lr, rinfo = refbin.search(path, c["metric"], q[:nq], K, ef, 100, threads=cores, reps=2)
@@ -118,7 +132,10 @@ def main():
             row["speedup"] = row["qps"] / row["ref_qps"]
         rows.append(row)
         print("[sweep]", json.dumps(row), flush=True)
+    ok = [r for r in rows if r["recall"] >= 0.95]
+    operating_point = min(ok, key=lambda r: r["ef"]) if ok else None
     out = dict(config=args.config, params={k: v for k, v in c.items() if k != "efs"}, index_build=binfo,
+               operating_point_recall_095=operating_point,
                bruteforce=bf, peak_gbs=pk, peak_source=pk_src, host_cores=cores, rows=rows)
     if args.out:
         os.makedirs(os.path.dirname(os.path.abspath(args.out)), exist_ok=True)
