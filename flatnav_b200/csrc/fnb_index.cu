@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -11,6 +13,7 @@
 #include <limits>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/flatnav_b200.h"
@@ -251,6 +254,9 @@ static int new_lane(Lane** out) {
     free_lane(l);
     return fail(FNB_ERR_CUDA, "cannot map the lane's pinned block");
   }
+  l->h_flag = reinterpret_cast<volatile uint32_t*>(l->h_totals + 7);
+  *l->h_flag = 0u;
+  l->h_flag_dev = reinterpret_cast<unsigned int*>(l->h_totals_dev + 7);
   l->h_marks = reinterpret_cast<uint32_t*>(l->h_totals + 8);
   l->h_marks[FNB_FEED_CHUNKS] = 0xffffffffu;  // "everything is there": releases a launch whose feeding was cut short
   *out = l;
@@ -293,16 +299,19 @@ struct LaneHold {
   Replica* r = nullptr;
   Lane* l = nullptr;
   bool feeding = false;  // a host-fed launch has not been fed to the end yet
+  bool drained = false;  // the lane's launch was seen to finish (its flag in pinned memory): nothing is left on the stream
   LaneHold() = default;
   LaneHold(const LaneHold&) = delete;
   LaneHold& operator=(const LaneHold&) = delete;
-  LaneHold(LaneHold&& o) noexcept : r(o.r), l(o.l), feeding(o.feeding) { o.l = nullptr; }
+  LaneHold(LaneHold&& o) noexcept : r(o.r), l(o.l), feeding(o.feeding), drained(o.drained) { o.l = nullptr; }
   ~LaneHold() {
     if (!l) return;
-    cudaSetDevice(r->device);
-    // leaving early (an error after the launch): let the waiting warps through, the call fails anyway
-    if (feeding) cudaMemcpyAsync(l->q_ready, l->h_marks + FNB_FEED_CHUNKS, 4, cudaMemcpyHostToDevice, l->copy_stream);
-    cudaStreamSynchronize(l->stream);
+    if (!drained) {
+      cudaSetDevice(r->device);
+      // leaving early (an error after the launch): let the waiting warps through, the call fails anyway
+      if (feeding) cudaMemcpyAsync(l->q_ready, l->h_marks + FNB_FEED_CHUNKS, 4, cudaMemcpyHostToDevice, l->copy_stream);
+      cudaStreamSynchronize(l->stream);
+    }
     release_lane(*r, l);
   }
 };
@@ -713,6 +722,8 @@ int fnb_search(fnb_index* ix, const void* queries, int64_t Q, int K, int ef_sear
   static const bool no_zero_copy = getenv("FNB_NO_ZEROCOPY") != nullptr;
   static const bool no_staging = getenv("FNB_NO_STAGING") != nullptr;
   static const bool no_feed = getenv("FNB_NO_FEED") != nullptr;
+  static const bool no_flag = getenv("FNB_NO_FLAG_WAIT") != nullptr;
+  static const bool time_kernels = getenv("FNB_TIME_KERNELS") != nullptr;
   static const size_t stage_max = getenv("FNB_STAGE_MAX") ? (size_t)atoll(getenv("FNB_STAGE_MAX")) : ((size_t)64 << 20);
   auto mapped = [](const void* host) -> unsigned char* {
     cudaPointerAttributes a;
@@ -722,14 +733,18 @@ int fnb_search(fnb_index* ix, const void* queries, int64_t Q, int K, int ef_sear
     }
     return a.type == cudaMemoryTypeHost ? static_cast<unsigned char*>(a.devicePointer) : nullptr;
   };
-  unsigned char* zq = no_zero_copy ? nullptr : mapped(queries);
-  unsigned char* zd = no_zero_copy ? nullptr : mapped(out_dist);
-  unsigned char* zl = no_zero_copy ? nullptr : mapped(out_label);
+  // (a latency batch always goes through the lane's pinned block: no pointer queries — three driver calls under the
+  // context lock — on the path that concurrent single-query callers share)
+  const bool probe = !no_zero_copy && !p0.lat;
+  unsigned char* zq = probe ? mapped(queries) : nullptr;
+  unsigned char* zd = probe ? mapped(out_dist) : nullptr;
+  unsigned char* zl = probe ? mapped(out_label) : nullptr;
   if (!zd || !zl) zd = zl = nullptr;
   const int64_t per = (Q + R - 1) / R;
   struct Part {
     int64_t q0 = 0, nq = 0;
-    bool stage_out = false, counters_in_block = false;
+    bool stage_out = false, counters_in_block = false, by_flag = false, timed = true;
+    uint32_t seq = 0;
     size_t off_dist = 0, off_label = 0, off_nd = 0, off_nh = 0, off_len = 0;
   };
   std::vector<Part> parts(R);
@@ -808,22 +823,34 @@ int fnb_search(fnb_index* ix, const void* queries, int64_t Q, int K, int ef_sear
     }
     if (q_in_block) memcpy(ln.h_pinned, q_src, qb);
     if (feed) p.q_ready = ln.q_ready;
-    CU(cudaEventRecord(ln.ev[0], ln.stream));
+    // Completion: when nothing follows the kernel on the stream (results land in pinned memory by the kernel's own
+    // stores) the host waits for a flag the kernel's last warp writes to pinned memory instead of synchronising the
+    // stream — no driver call, no lock shared with other calling threads.  Device-side timing (4 event records per
+    // call) is kept for throughput batches and dropped for latency batches unless FNB_TIME_KERNELS=1.
+    pt.by_flag = !no_flag && (zd || pt.stage_out);
+    pt.timed = !p.lat || time_kernels || !pt.by_flag;
+    if (pt.by_flag) {
+      if (!p.done) p.done = ln.counter + FNB_SLOT_DONE / 4;  // latency batches: no counter / totals, but the last-CTA epilogue
+      p.done_seq = ln.h_flag_dev;
+      p.seq = ++ln.seq ? ln.seq : ++ln.seq;
+      pt.seq = p.seq;
+    }
+    if (pt.timed) CU(cudaEventRecord(ln.ev[0], ln.stream));
     if (!zq && !q_in_block && !feed) CU(cudaMemcpyAsync(d_q, q_src, qb, cudaMemcpyHostToDevice, ln.stream));
     if (feed) {
       CU(cudaMemsetAsync(ln.q_ready, 0, 4, ln.stream));
       CU(cudaEventRecord(ln.ev_feed, ln.stream));  // the first watermark must not land before the clear above
       CU(cudaStreamWaitEvent(ln.copy_stream, ln.ev_feed, 0));
     }
-    CU(cudaEventRecord(ln.ev[1], ln.stream));
+    if (pt.timed) CU(cudaEventRecord(ln.ev[1], ln.stream));
     cudaError_t e = dispatch_search(ix, p, r.num_sms, ln.stream);
     if (e != cudaSuccess) return fail(FNB_ERR_CUDA, "search kernel launch failed: %s", cudaGetErrorString(e));
-    CU(cudaEventRecord(ln.ev[2], ln.stream));
+    if (pt.timed) CU(cudaEventRecord(ln.ev[2], ln.stream));
     if (!zd && !pt.stage_out) {
       CU(cudaMemcpyAsync(out_dist + (size_t)pt.q0 * K, d_dist, ob, cudaMemcpyDeviceToHost, ln.stream));
       CU(cudaMemcpyAsync(out_label + (size_t)pt.q0 * K, d_label, ob, cudaMemcpyDeviceToHost, ln.stream));
     }
-    CU(cudaEventRecord(ln.ev[3], ln.stream));
+    if (pt.timed) CU(cudaEventRecord(ln.ev[3], ln.stream));
     if (feed) {
       // a pageable cudaMemcpyAsync returns once the chunk is staged, so this loop paces itself against the host copy
       // while the DMA of earlier chunks and the traversal of the queries already there proceed
@@ -851,10 +878,35 @@ int fnb_search(fnb_index* ix, const void* queries, int64_t Q, int K, int ef_sear
     Replica& r = ix->replicas[i];
     Lane& ln = *held[i].l;
     CU(cudaSetDevice(r.device));
-    CU(cudaStreamSynchronize(ln.stream));
+    if (pt.by_flag) {
+      // spin on the pinned word; after a while let other threads of an oversubscribed host run; after 2 s fall back to
+      // the stream (a failed launch never writes the flag: the synchronise reports the error)
+      const auto t0 = std::chrono::steady_clock::now();
+      for (uint32_t spins = 0; *ln.h_flag != pt.seq; spins++) {
+        if (spins < 4096u) {
+#if defined(__x86_64__) || defined(__i386__)
+          __builtin_ia32_pause();
+#endif
+          continue;
+        }
+        std::this_thread::yield();
+        if ((spins & 1023u) == 0u && std::chrono::steady_clock::now() - t0 > std::chrono::seconds(2)) {
+          CU(cudaStreamSynchronize(ln.stream));
+          break;
+        }
+      }
+      std::atomic_thread_fence(std::memory_order_acquire);
+      held[i].drained = true;
+      if (pt.timed) CU(cudaEventSynchronize(ln.ev[3]));  // returns at once: the kernel is done, the record is all that is left
+    } else {
+      CU(cudaStreamSynchronize(ln.stream));
+      held[i].drained = true;
+    }
     float a = 0.f, b = 0.f;
-    CU(cudaEventElapsedTime(&a, ln.ev[1], ln.ev[2]));
-    CU(cudaEventElapsedTime(&b, ln.ev[0], ln.ev[3]));
+    if (pt.timed) {
+      CU(cudaEventElapsedTime(&a, ln.ev[1], ln.ev[2]));
+      CU(cudaEventElapsedTime(&b, ln.ev[0], ln.ev[3]));
+    }
     if (pt.stage_out) {
       const size_t ob = (size_t)pt.nq * K * 4;
       memcpy(out_dist + (size_t)pt.q0 * K, ln.h_pinned + pt.off_dist, ob);

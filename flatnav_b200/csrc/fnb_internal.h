@@ -34,6 +34,9 @@ struct Lane {
   unsigned int* q_ready = nullptr;         // device: watermark of a host-fed batch (queries already copied in)
   unsigned long long* h_totals = nullptr;  // pinned: the kernel's last warp writes the totals of the launch here
   unsigned long long* h_totals_dev = nullptr;  // its device-side alias
+  volatile uint32_t* h_flag = nullptr;     // pinned: sequence number of the lane's last launch that has finished
+  unsigned int* h_flag_dev = nullptr;      // its device-side alias
+  uint32_t seq = 0;                        // launches made on this lane
   uint32_t* h_marks = nullptr;             // pinned: the watermark values a host-fed batch copies to q_ready, [FNB_FEED_CHUNKS + 1]
   cudaStream_t copy_stream = nullptr;      // feeds the queries of a pageable caller while the kernel runs on `stream`
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};

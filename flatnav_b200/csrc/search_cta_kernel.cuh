@@ -4,9 +4,9 @@
 //
 // A lone warp walking the graph is bound by instruction latency, not by HBM: one hop of the single-warp latency variant
 // costs ~890 dependent-ish instructions at ~7 cycles each, of which only ~1.8 are memory waits (profiles/r1_lat_*),
-// 3.1 us per hop against 1.7 us for one CPU thread of the reference.  Here four warps share one query:
+// 3.1 us per hop against 1.7 us for one CPU thread of the reference.  Here five warps share one query:
 //   * warp 0 drives: pick, adjacency row, visited filter, list merge;
-//   * all four warps fetch and evaluate the fresh rows of the expansion, a quarter each, every warp with ALL its rows in
+//   * warps 1..4 fetch and evaluate the fresh rows of the expansion, a quarter each, every warp with ALL its rows in
 //     flight at once (registers are free at one CTA per query) — one HBM round trip per hop;
 //   * the hop is software-pipelined: the next node to expand is min(first unexpanded list entry, smallest accepted
 //     candidate), which is known BEFORE the accepted candidates are merged into the list.  So the driver first starts
@@ -23,30 +23,31 @@
 
 namespace fnb {
 
-#define FNB_CTA_WARPS 4
+#define FNB_CTA_WARPS 5    // warp 0 drives, warps 1..4 evaluate rows
+#define FNB_CTA_WORKERS 4
 // warp-wide load batches one warp holds in registers in the CTA kernel: a quarter of 32 rows if the staging registers
 // (NB x CH uint4 per lane) allow — 24 uint4 for rows of up to 512 B, 16 for the whole-warp-per-row shapes, whose query
 // alone takes up to 16 uint4 per lane
 __host__ __device__ constexpr int fnb_cta_batches(int g, int ch) {
-  const int want = 32 / (32 / g) / FNB_CTA_WARPS < 1 ? 1 : 32 / (32 / g) / FNB_CTA_WARPS;  // batches of a quarter of 32 rows
+  const int want = 32 / (32 / g) / FNB_CTA_WORKERS < 1 ? 1 : 32 / (32 / g) / FNB_CTA_WORKERS;  // batches of a quarter of 32 rows
   const int cap = (g == 32 ? 16 : 24) / ch < 1 ? 1 : (g == 32 ? 16 : 24) / ch;
   return want < cap ? want : cap;
 }
 
-// Rows ids[0..n) (shared memory), a quarter per warp: batch b (RPI rows) belongs to warp b % 4.  Same arithmetic and
-// reduction order as batch_distance.  Distances go to dist[0..n) in shared memory.
+// Rows ids[0..n) (shared memory), a quarter per worker warp: batch b (RPI rows) belongs to worker b % 4.  Same arithmetic
+// and reduction order as batch_distance.  Distances go to dist[0..n) in shared memory.
 template <int DT, int METRIC, int G, int CH, bool EXACT>
 __device__ __forceinline__ void cta_rows(const SearchParams& p, const uint4 (&q)[CH], const uint32_t* ids, uint32_t n,
-                                         float* dist, int warp, int lane) {
+                                         float* dist, int worker, int lane) {
   typedef Arith<DT, METRIC> A;
   constexpr int RPI = 32 / G;
   constexpr int NB = fnb_cta_batches(G, CH);
   const int g = lane / G, pos = lane % G;
-  for (uint32_t b0 = (uint32_t)warp; b0 * RPI < n; b0 += FNB_CTA_WARPS * NB) {
+  for (uint32_t b0 = (uint32_t)worker; b0 * RPI < n; b0 += FNB_CTA_WORKERS * NB) {
     uint4 x[NB][CH];
 #pragma unroll
     for (int u = 0; u < NB; u++) {
-      const uint32_t c = (b0 + (uint32_t)u * FNB_CTA_WARPS) * RPI + (uint32_t)g;
+      const uint32_t c = (b0 + (uint32_t)u * FNB_CTA_WORKERS) * RPI + (uint32_t)g;
       const bool ok = c < n;
       const uint32_t rid = ids[ok ? c : 0];
       const uint4* row = p.vec + (size_t)rid * p.stride + pos;
@@ -55,8 +56,8 @@ __device__ __forceinline__ void cta_rows(const SearchParams& p, const uint4 (&q)
     }
 #pragma unroll
     for (int u = 0; u < NB; u++) {
-      const uint32_t c = (b0 + (uint32_t)u * FNB_CTA_WARPS) * RPI + (uint32_t)g;
-      if ((b0 + (uint32_t)u * FNB_CTA_WARPS) * RPI < n) {  // warp-uniform
+      const uint32_t c = (b0 + (uint32_t)u * FNB_CTA_WORKERS) * RPI + (uint32_t)g;
+      if ((b0 + (uint32_t)u * FNB_CTA_WORKERS) * RPI < n) {  // warp-uniform
         typename A::acc_t acc = 0;
 #pragma unroll
         for (int k = 0; k < CH; k++)
@@ -67,6 +68,14 @@ __device__ __forceinline__ void cta_rows(const SearchParams& p, const uint4 (&q)
       }
     }
   }
+}
+
+// Block-wide barrier between the driver and the workers.  A named barrier with an explicit thread count rather than
+// __syncthreads(): the driver and the workers reach it from different places in the code (the usual producer / consumer
+// arrangement of a warp-specialised kernel), which bar.sync counts correctly and __syncthreads() does not promise.
+__device__ __forceinline__ void cta_sync() {
+  __syncwarp();  // bar.sync is warp-aligned: reconverge first (inline asm does not make the compiler do it)
+  asm volatile("bar.sync 1, %0;" ::"n"(FNB_CTA_WARPS * 32) : "memory");
 }
 
 __device__ __forceinline__ uint64_t warp_min_u64(uint64_t v) {
@@ -97,11 +106,11 @@ __global__ void __launch_bounds__(FNB_CTA_WARPS * 32, 2) fnb_search_cta_kernel(c
     if (warp != 0) {
       // ---- workers: evaluate their quarter of every published round of rows ----
       for (;;) {
-        __syncthreads();  // A: ids / ctl[0] published
+        cta_sync();  // A: ids / ctl[0] published
         const uint32_t n = ctl[0];
         if (n == 0xffffffffu) break;
-        cta_rows<DT, METRIC, G, CH, EXACT>(p, q, ids, n, dist, warp, lane);
-        __syncthreads();  // B: distances in place
+        cta_rows<DT, METRIC, G, CH, EXACT>(p, q, ids, n, dist, warp - 1, lane);
+        cta_sync();  // B: distances in place
       }
     } else {
       visited_clear(tab, p.vs_buckets, lane);
@@ -114,9 +123,8 @@ __global__ void __launch_bounds__(FNB_CTA_WARPS * 32, 2) fnb_search_cta_kernel(c
           const uint32_t n = min(32u, p.nprobe - base);
           if (pi < p.nprobe) ids[lane] = pi * p.step;
           if (lane == 0) ctl[0] = n;
-          __syncthreads();  // A
-          cta_rows<DT, METRIC, G, CH, EXACT>(p, q, ids, n, dist, 0, lane);
-          __syncthreads();  // B
+          cta_sync();  // A
+          cta_sync();  // B
           if (pi < p.nprobe) {
             const uint64_t k = ((uint64_t)ord_f32(dist[lane]) << 32) | pi;
             best = k < best ? k : best;
@@ -153,15 +161,14 @@ __global__ void __launch_bounds__(FNB_CTA_WARPS * 32, 2) fnb_search_cta_kernel(c
             }
             if (n) {
               if (lane == 0) ctl[0] = n;
-              __syncthreads();  // A: the workers start fetching
+              cta_sync();  // A: the workers start fetching
             }
             // the previous round's accepted candidates go into the list while this round's rows are in flight
             if (__any_sync(FNB_FULL, pacc)) merge_accepted(list, len, start, p.B, p.Bpow2, pkey, pacc, lane);
             pacc = false;
             if (!n) continue;
             ndist += n;
-            cta_rows<DT, METRIC, G, CH, EXACT>(p, q, ids, n, dist, 0, lane);
-            __syncthreads();  // B
+            cta_sync();  // B
             const bool full = len >= p.B;
             const uint32_t worst_hi = (uint32_t)(list[len - 1] >> 32);
             pkey = make_key(fresh ? dist[myrank] : 0.f, nb);
@@ -198,6 +205,7 @@ __global__ void __launch_bounds__(FNB_CTA_WARPS * 32, 2) fnb_search_cta_kernel(c
             if (pacc && pkey == kmin) pkey |= 1ull;  // enters the list as expanded (a duplicated link: both copies, one is dropped)
           } else if (e_list != ~0ull) {
             cur = (uint32_t)e_list >> 1;
+            __syncwarp();  // every lane has read its entries of the scan above
             if (lane == 0) list[i_list] = e_list | 1ull;
             start = i_list;
             __syncwarp();
@@ -207,7 +215,7 @@ __global__ void __launch_bounds__(FNB_CTA_WARPS * 32, 2) fnb_search_cta_kernel(c
         }
       }
       if (lane == 0) ctl[0] = 0xffffffffu;
-      __syncthreads();  // A: releases the workers from this query
+      cta_sync();  // A: releases the workers from this query
 
       // ---- output: ascending distance, label field of the node (Index.h:393-406) ----
       asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -233,11 +241,11 @@ __global__ void __launch_bounds__(FNB_CTA_WARPS * 32, 2) fnb_search_cta_kernel(c
         }
       }
     }
-    __syncthreads();  // the next query of this CTA reuses the shared memory
+    cta_sync();  // the next query of this CTA reuses the shared memory
   }
   asm volatile("griddepcontrol.wait;" ::: "memory");
   if (p.done && threadIdx.x == 0) {
-    __threadfence();
+    __threadfence_system();  // this CTA's results (possibly in pinned host memory) before its count
     if (atomicAdd(p.done, 1u) == gridDim.x - 1u) {  // the last CTA of the grid: publish the totals, leave the slot clean
       __threadfence();
       if (p.totals) {
@@ -247,8 +255,8 @@ __global__ void __launch_bounds__(FNB_CTA_WARPS * 32, 2) fnb_search_cta_kernel(c
       }
       if (p.counter) *p.counter = 0u;
       *p.done = 0u;
-      __threadfence();
-      if (p.done_seq) *p.done_seq = p.seq;
+      __threadfence_system();
+      if (p.done_seq) *p.done_seq = p.seq;  // the host may be polling this word instead of synchronising the stream
     }
   }
 }

@@ -694,7 +694,7 @@ __global__ void __launch_bounds__(LAT ? 32 : FNB_WARPS_PER_CTA * 32, LAT ? 1 : (
   }
   asm volatile("griddepcontrol.wait;" ::: "memory");  // also by warps that found no work: launches complete in stream order
   if (p.done && lane == 0) {
-    __threadfence();
+    __threadfence_system();  // this warp's results (possibly in pinned host memory) before its count
     const unsigned int n_warps = gridDim.x * (LAT ? 1u : (unsigned int)FNB_WARPS_PER_CTA);
     if (atomicAdd(p.done, 1u) == n_warps - 1u) {  // the last warp of the grid
       __threadfence();
@@ -705,8 +705,8 @@ __global__ void __launch_bounds__(LAT ? 32 : FNB_WARPS_PER_CTA * 32, LAT ? 1 : (
       }
       if (p.counter) *p.counter = 0u;
       *p.done = 0u;
-      __threadfence();
-      if (p.done_seq) *p.done_seq = p.seq;
+      __threadfence_system();
+      if (p.done_seq) *p.done_seq = p.seq;  // the host may be polling this word instead of synchronising the stream
     }
   }
 }

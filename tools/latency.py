@@ -76,7 +76,12 @@ def main() -> None:
     ap.add_argument("--paper", action="store_true",
                     help="the authors' settings (experiments/Makefile:8-22, run-benchmark.py:44): k = 100, "
                          "ef_search in {100, 200, 300, 500, 1000, 3000}")
+    ap.add_argument("--time-kernels", action="store_true",
+                    help="also record the device time of every search_single launch (FNB_TIME_KERNELS=1: four event "
+                         "records per call, which the protocol numbers then include)")
     args = ap.parse_args()
+    if args.time_kernels:
+        os.environ["FNB_TIME_KERNELS"] = "1"
     if args.paper:
         args.k = args.k or 100
         args.efs = "100,200,300,500,1000,3000"
@@ -104,11 +109,12 @@ def main() -> None:
         ef = max(ef, 1)
         single = compute_metrics(ix, queries, gt, ef, K)
         # kernel-only view of one query: device time between the events fnb_search records around its launch
-        kms = []
-        for q in queries[:500]:
-            ix.search_single(q, K, ef)
-            kms.append(ix.last_stats["kernel_ms"])
-        single["kernel_ms_p50"] = float(np.percentile(kms, 50))
+        if args.time_kernels:
+            kms = []
+            for q in queries[:500]:
+                ix.search_single(q, K, ef)
+                kms.append(ix.last_stats["kernel_ms"])
+            single["kernel_ms_p50"] = float(np.percentile(kms, 50))
         t0 = time.time()
         _, lab = ix.search(queries, K, ef)
         batched = {"qps": len(queries) / (time.time() - t0), "recall": compute_recall(gt, lab, K)}
