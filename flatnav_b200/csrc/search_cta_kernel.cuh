@@ -70,12 +70,34 @@ __device__ __forceinline__ void cta_rows(const SearchParams& p, const uint4 (&q)
   }
 }
 
-// Block-wide barrier between the driver and the workers.  A named barrier with an explicit thread count rather than
-// __syncthreads(): the driver and the workers reach it from different places in the code (the usual producer / consumer
-// arrangement of a warp-specialised kernel), which bar.sync counts correctly and __syncthreads() does not promise.
+// Hand-off between the driver and the workers: two named barriers used as producer / consumer pairs (PTX bar.arrive /
+// bar.sync with an explicit thread count — the arrangement of a warp-specialised kernel; the two sides reach them from
+// different places in the code, which __syncthreads() does not promise to support):
+//   barrier 1 "rows published":  the driver ARRIVES (it does not wait), the workers wait;
+//   barrier 2 "distances ready": the workers ARRIVE, the driver waits.
+// A worker cannot run ahead: after arriving at 2 it waits at 1, which needs the driver, who first waits at 2.
+// Barrier 3 is the plain all-threads barrier at the end of a query.  bar.* are warp-aligned: reconverge first (inline
+// asm does not make the compiler do it).
+#define FNB_CTA_THREADS (FNB_CTA_WARPS * 32)
+__device__ __forceinline__ void rows_published_arrive() {
+  __syncwarp();
+  asm volatile("bar.arrive 1, %0;" ::"n"(FNB_CTA_THREADS) : "memory");
+}
+__device__ __forceinline__ void rows_published_wait() {
+  __syncwarp();
+  asm volatile("bar.sync 1, %0;" ::"n"(FNB_CTA_THREADS) : "memory");
+}
+__device__ __forceinline__ void distances_ready_arrive() {
+  __syncwarp();
+  asm volatile("bar.arrive 2, %0;" ::"n"(FNB_CTA_THREADS) : "memory");
+}
+__device__ __forceinline__ void distances_ready_wait() {
+  __syncwarp();
+  asm volatile("bar.sync 2, %0;" ::"n"(FNB_CTA_THREADS) : "memory");
+}
 __device__ __forceinline__ void cta_sync() {
-  __syncwarp();  // bar.sync is warp-aligned: reconverge first (inline asm does not make the compiler do it)
-  asm volatile("bar.sync 1, %0;" ::"n"(FNB_CTA_WARPS * 32) : "memory");
+  __syncwarp();
+  asm volatile("bar.sync 3, %0;" ::"n"(FNB_CTA_THREADS) : "memory");
 }
 
 __device__ __forceinline__ uint64_t warp_min_u64(uint64_t v) {
@@ -106,11 +128,11 @@ __global__ void __launch_bounds__(FNB_CTA_WARPS * 32, 2) fnb_search_cta_kernel(c
     if (warp != 0) {
       // ---- workers: evaluate their quarter of every published round of rows ----
       for (;;) {
-        cta_sync();  // A: ids / ctl[0] published
+        rows_published_wait();
         const uint32_t n = ctl[0];
         if (n == 0xffffffffu) break;
         cta_rows<DT, METRIC, G, CH, EXACT>(p, q, ids, n, dist, warp - 1, lane);
-        cta_sync();  // B: distances in place
+        distances_ready_arrive();
       }
     } else {
       visited_clear(tab, p.vs_buckets, lane);
@@ -123,8 +145,8 @@ __global__ void __launch_bounds__(FNB_CTA_WARPS * 32, 2) fnb_search_cta_kernel(c
           const uint32_t n = min(32u, p.nprobe - base);
           if (pi < p.nprobe) ids[lane] = pi * p.step;
           if (lane == 0) ctl[0] = n;
-          cta_sync();  // A
-          cta_sync();  // B
+          rows_published_arrive();
+          distances_ready_wait();
           if (pi < p.nprobe) {
             const uint64_t k = ((uint64_t)ord_f32(dist[lane]) << 32) | pi;
             best = k < best ? k : best;
@@ -161,14 +183,14 @@ __global__ void __launch_bounds__(FNB_CTA_WARPS * 32, 2) fnb_search_cta_kernel(c
             }
             if (n) {
               if (lane == 0) ctl[0] = n;
-              cta_sync();  // A: the workers start fetching
+              rows_published_arrive();  // the workers start fetching
             }
             // the previous round's accepted candidates go into the list while this round's rows are in flight
             if (__any_sync(FNB_FULL, pacc)) merge_accepted(list, len, start, p.B, p.Bpow2, pkey, pacc, lane);
             pacc = false;
             if (!n) continue;
             ndist += n;
-            cta_sync();  // B
+            distances_ready_wait();
             const bool full = len >= p.B;
             const uint32_t worst_hi = (uint32_t)(list[len - 1] >> 32);
             pkey = make_key(fresh ? dist[myrank] : 0.f, nb);
@@ -215,7 +237,7 @@ __global__ void __launch_bounds__(FNB_CTA_WARPS * 32, 2) fnb_search_cta_kernel(c
         }
       }
       if (lane == 0) ctl[0] = 0xffffffffu;
-      cta_sync();  // A: releases the workers from this query
+      rows_published_arrive();  // releases the workers from this query
 
       // ---- output: ascending distance, label field of the node (Index.h:393-406) ----
       asm volatile("griddepcontrol.wait;" ::: "memory");
