@@ -692,7 +692,11 @@ def main() -> None:
                          "launches": "adjacent on one stream, programmatic dependent launch (the next step's CTAs fill "
                                      "the tail of the previous one)",
                          "isolated_launch_ms": single_ms, "isolated_launch_qps": world * Q / (single_ms * 1e-3),
-                         "isolated_launch_frac": ab / (single_ms * 1e-3) / 1e9 / peak},
+                         "isolated_launch_frac": ab / (single_ms * 1e-3) / 1e9 / peak,
+                         "dram_side_frac": (traffic / (single_ms * 1e-3) / 1e9 / peak) if traffic else None,
+                         "note": "algorithmic bytes count every evaluated row, L2-served ones included (the 100 entry-probe "
+                                 "rows every query reads, adjacency rows prefetched a hop earlier), so frac may exceed 1; "
+                                 "dram_side_frac = traffic / isolated launch time / peak"},
             "sustained": sustained, "strong_scaling": strong, "sharded": sharded,
         }
         if not line["recall_ok"]:

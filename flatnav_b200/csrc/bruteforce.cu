@@ -155,11 +155,19 @@ extern "C" int fnb_bruteforce(fnb_index* ix, const void* queries, int64_t Q, int
     }                                                                                                 \
   } while (0)
   BF_CU(cudaSetDevice(r.device));
-  unsigned char *d_q = nullptr, *d_d = nullptr, *d_l = nullptr;
+  struct DevBufs {  // freed on every way out, error returns included
+    unsigned char *q = nullptr, *d = nullptr, *l = nullptr;
+    ~DevBufs() {
+      cudaFree(q);
+      cudaFree(d);
+      cudaFree(l);
+    }
+  } bufs;
   const size_t qb = (size_t)Q * h.data_size, ob = (size_t)Q * K * 4;
-  BF_CU(cudaMalloc(&d_q, qb));
-  BF_CU(cudaMalloc(&d_d, ob));
-  BF_CU(cudaMalloc(&d_l, ob));
+  BF_CU(cudaMalloc(&bufs.q, qb));
+  BF_CU(cudaMalloc(&bufs.d, ob));
+  BF_CU(cudaMalloc(&bufs.l, ob));
+  unsigned char *d_q = bufs.q, *d_d = bufs.d, *d_l = bufs.l;
   BF_CU(cudaMemcpyAsync(d_q, queries, qb, cudaMemcpyHostToDevice, r.stream));
   // FNB_BF_MODE=exact|tensor forces a path (tests, profiling); default: the tcgen05 filter + exact re-rank
   // whenever the problem is large enough to fill tensor-core tiles.
@@ -207,9 +215,6 @@ extern "C" int fnb_bruteforce(fnb_index* ix, const void* queries, int64_t Q, int
     BF_CU(cudaMemcpyAsync(out_label, d_l, ob, cudaMemcpyDeviceToHost, r.stream));
     BF_CU(cudaStreamSynchronize(r.stream));
   }
-  cudaFree(d_q);
-  cudaFree(d_d);
-  cudaFree(d_l);
   cudaSetDevice(prev);
   g_last_bf = run;
   return rc;

@@ -164,7 +164,11 @@ static int upload_replica(const Header& h, const unsigned char* blob, int device
   const uint32_t stride = row_stride_chunks(nchunks);
   const uint64_t n = h.cur_nodes ? h.cur_nodes : 1;
   const uint64_t blob_bytes = h.node_size * h.cur_nodes;
-  unsigned char* d_blob = nullptr;
+  struct Blob {  // the device copy of the file image: freed on every way out
+    unsigned char* p = nullptr;
+    ~Blob() { cudaFree(p); }
+  } blob_guard;
+  unsigned char*& d_blob = blob_guard.p;
   CU(cudaMalloc(&r->vec, n * stride * FNB_CHUNK_BYTES));
   CU(cudaMalloc(&r->adj, n * h.M * 4));
   CU(cudaMalloc(&r->labels, n * 4));
@@ -195,7 +199,6 @@ static int upload_replica(const Header& h, const unsigned char* blob, int device
     unsigned int bad = 0;
     CU(cudaMemcpyAsync(&bad, r->counter, 4, cudaMemcpyDeviceToHost, r->stream));
     CU(cudaStreamSynchronize(r->stream));
-    CU(cudaFree(d_blob));
     if (bad) return fail(FNB_ERR_FORMAT, "%u links point outside [0, cur_num_nodes)", bad);
   }
   return FNB_OK;
@@ -825,10 +828,10 @@ int fnb_search(fnb_index* ix, const void* queries, int64_t Q, int K, int ef_sear
     if (feed) p.q_ready = ln.q_ready;
     // Completion: when nothing follows the kernel on the stream (results land in pinned memory by the kernel's own
     // stores) the host waits for a flag the kernel's last warp writes to pinned memory instead of synchronising the
-    // stream — no driver call, no lock shared with other calling threads.  Device-side timing (4 event records per
-    // call) is kept for throughput batches and dropped for latency batches unless FNB_TIME_KERNELS=1.
+    // stream — no driver call, no lock shared with other calling threads.  Device-side timing (stats->kernel_ms /
+    // total_ms: four event records and a query per call) is then off unless FNB_TIME_KERNELS=1.
     pt.by_flag = !no_flag && (zd || pt.stage_out);
-    pt.timed = !p.lat || time_kernels || !pt.by_flag;
+    pt.timed = time_kernels || !pt.by_flag;
     if (pt.by_flag) {
       if (!p.done) p.done = ln.counter + FNB_SLOT_DONE / 4;  // latency batches: no counter / totals, but the last-CTA epilogue
       p.done_seq = ln.h_flag_dev;

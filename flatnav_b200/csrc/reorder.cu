@@ -316,21 +316,30 @@ static int download_links(const fnb_index* ix, std::vector<uint32_t>* links) {
   return FNB_OK;
 }
 
+// Two phases, so that replicas can never end up permuted differently: every replica first builds its re-laid-out
+// arrays out of place; only when all of them succeeded are the arrays swapped in.  A failure on any replica frees what
+// was built and leaves the whole index as it was.
 static int apply_perm(fnb_index* ix, const uint32_t* perm) {
   const Header& h = ix->h;
   const uint32_t n = (uint32_t)h.cur_nodes;
   if (!n) return FNB_OK;
+  struct NewArrays {
+    int device = -1;
+    uint4* vec = nullptr;
+    uint32_t* adj = nullptr;
+    int32_t* labels = nullptr;
+  };
+  std::vector<NewArrays> built(ix->replicas.size());
   int prev = 0;
   cudaGetDevice(&prev);
-  for (Replica& r : ix->replicas) {
-    std::vector<void*> tmp;
+  auto build_one = [&](Replica& r, NewArrays& out) -> int {
+    std::vector<void*> tmp;  // R_CU frees these on failure
     R_CU(cudaSetDevice(r.device));
+    out.device = r.device;
     cudaStream_t s = r.stream;
     const size_t rowb = (size_t)ix->stride * FNB_CHUNK_BYTES;
-    uint32_t *d_perm = nullptr, *d_seen = nullptr, *adj = nullptr;
+    uint32_t *d_perm = nullptr, *d_seen = nullptr;
     unsigned int* d_bad = nullptr;
-    uint4* vec = nullptr;
-    int32_t* labels = nullptr;
     R_CU(cudaMalloc(&d_perm, (size_t)n * 4));
     tmp.push_back(d_perm);
     R_CU(cudaMalloc(&d_seen, ((size_t)n / 32 + 1) * 4));
@@ -351,25 +360,46 @@ static int apply_perm(fnb_index* ix, const uint32_t* perm) {
       return fail(FNB_ERR_INVALID_ARG, "not a permutation of [0, %u): %u entries out of range or repeated", n, bad);
     }
     // out of place into arrays of the same capacity (construction may have reserved more rows than are in use)
-    R_CU(cudaMalloc(&vec, r.capacity * rowb));
-    tmp.push_back(vec);
-    R_CU(cudaMalloc(&adj, r.capacity * h.M * 4));
-    tmp.push_back(adj);
-    R_CU(cudaMalloc(&labels, r.capacity * 4));
-    tmp.push_back(labels);
-    relabel_kernel<<<r.num_sms * 16, 256, 0, s>>>(r.vec, r.adj, r.labels, d_perm, n, (uint32_t)h.M, ix->stride, vec, adj,
-                                                  labels);
+    R_CU(cudaMalloc(&out.vec, r.capacity * rowb));
+    tmp.push_back(out.vec);
+    R_CU(cudaMalloc(&out.adj, r.capacity * h.M * 4));
+    tmp.push_back(out.adj);
+    R_CU(cudaMalloc(&out.labels, r.capacity * 4));
+    tmp.push_back(out.labels);
+    relabel_kernel<<<r.num_sms * 16, 256, 0, s>>>(r.vec, r.adj, r.labels, d_perm, n, (uint32_t)h.M, ix->stride, out.vec,
+                                                  out.adj, out.labels);
     R_CU(cudaGetLastError());
     R_CU(cudaStreamSynchronize(s));
-    cudaFree(r.vec);
-    cudaFree(r.adj);
-    cudaFree(r.labels);
-    r.vec = vec;
-    r.adj = adj;
-    r.labels = labels;
     cudaFree(d_perm);
     cudaFree(d_seen);
     cudaFree(d_bad);
+    return FNB_OK;
+  };
+  for (size_t i = 0; i < ix->replicas.size(); i++) {
+    const int rc = build_one(ix->replicas[i], built[i]);
+    if (rc != FNB_OK) {
+      const std::string keep = g_last_error;
+      built[i] = NewArrays();  // its buffers were freed by the failing step
+      for (size_t k = 0; k < i; k++) {
+        cudaSetDevice(built[k].device);
+        cudaFree(built[k].vec);
+        cudaFree(built[k].adj);
+        cudaFree(built[k].labels);
+      }
+      cudaSetDevice(prev);
+      g_last_error = keep;
+      return rc;
+    }
+  }
+  for (size_t i = 0; i < ix->replicas.size(); i++) {
+    Replica& r = ix->replicas[i];
+    cudaSetDevice(r.device);
+    cudaFree(r.vec);
+    cudaFree(r.adj);
+    cudaFree(r.labels);
+    r.vec = built[i].vec;
+    r.adj = built[i].adj;
+    r.labels = built[i].labels;
   }
   cudaSetDevice(prev);
   return FNB_OK;

@@ -4,14 +4,16 @@
 //
 // A lone warp walking the graph is bound by instruction latency, not by HBM: one hop of the single-warp latency variant
 // costs ~890 dependent-ish instructions at ~7 cycles each, of which only ~1.8 are memory waits (profiles/r1_lat_*),
-// 3.1 us per hop against 1.7 us for one CPU thread of the reference.  Here five warps share one query:
-//   * warp 0 drives: pick, adjacency row, visited filter, list merge;
-//   * warps 1..4 fetch and evaluate the fresh rows of the expansion, a quarter each, every warp with ALL its rows in
-//     flight at once (registers are free at one CTA per query) — one HBM round trip per hop;
-//   * the hop is software-pipelined: the next node to expand is min(first unexpanded list entry, smallest accepted
-//     candidate), which is known BEFORE the accepted candidates are merged into the list.  So the driver first starts
-//     the next hop (adjacency, filter, row loads) and merges the previous hop's candidates while those rows are in
-//     flight; the merge (~28 % of a hop's instructions) leaves the critical path.
+// 3.1 us per hop against 1.7 us for one CPU thread of the reference.  Here six warps share one query, in three roles:
+//   * the driver (warp 0): pick, adjacency row, visited filter, acceptance test;
+//   * four workers (warps 1..4): fetch and evaluate the fresh rows of the expansion, a quarter each, every warp with ALL
+//     its rows in flight at once (registers are free at one CTA per query) — one HBM round trip per hop;
+//   * the merge warp (warp 5): owns the sorted list — inserts the accepted candidates, hands back the list length and
+//     the first unexpanded entry.
+//   The hop is software-pipelined: the next node to expand is min(first unexpanded list entry, smallest accepted
+//   candidate), which is known BEFORE the accepted candidates are merged into the list.  So the driver hands the
+//   candidates to the merge warp and goes straight on to the next hop (adjacency, filter, row fetch); the merge (~28 % of
+//   a hop's instructions in the one-warp variant) runs beside them and is waited for only before the next acceptance test.
 // Why this is the same search: a chosen candidate always survives the merge's truncation (it is smaller than the list's
 // worst entry, or the list is not full), and an old unexpanded entry that is the overall minimum cannot be truncated
 // away (all entries before it would have to be old and expanded, i.e. the list was longer than its capacity).  The
@@ -23,7 +25,7 @@
 
 namespace fnb {
 
-#define FNB_CTA_WARPS 5    // warp 0 drives, warps 1..4 evaluate rows
+#define FNB_CTA_WARPS 6    // warp 0 drives, warps 1..4 evaluate rows, warp 5 owns the list merge
 #define FNB_CTA_WORKERS 4
 // warp-wide load batches one warp holds in registers in the CTA kernel: a quarter of 32 rows if the staging registers
 // (NB x CH uint4 per lane) allow — 24 uint4 for rows of up to 512 B, 16 for the whole-warp-per-row shapes, whose query
@@ -79,25 +81,44 @@ __device__ __forceinline__ void cta_rows(const SearchParams& p, const uint4 (&q)
 // Barrier 3 is the plain all-threads barrier at the end of a query.  bar.* are warp-aligned: reconverge first (inline
 // asm does not make the compiler do it).
 #define FNB_CTA_THREADS (FNB_CTA_WARPS * 32)
+#define FNB_CTA_ROW_THREADS ((1 + FNB_CTA_WORKERS) * 32)  // the driver and the workers: the parties of barriers 1 and 2
 __device__ __forceinline__ void rows_published_arrive() {
   __syncwarp();
-  asm volatile("bar.arrive 1, %0;" ::"n"(FNB_CTA_THREADS) : "memory");
+  asm volatile("bar.arrive 1, %0;" ::"n"(FNB_CTA_ROW_THREADS) : "memory");
 }
 __device__ __forceinline__ void rows_published_wait() {
   __syncwarp();
-  asm volatile("bar.sync 1, %0;" ::"n"(FNB_CTA_THREADS) : "memory");
+  asm volatile("bar.sync 1, %0;" ::"n"(FNB_CTA_ROW_THREADS) : "memory");
 }
 __device__ __forceinline__ void distances_ready_arrive() {
   __syncwarp();
-  asm volatile("bar.arrive 2, %0;" ::"n"(FNB_CTA_THREADS) : "memory");
+  asm volatile("bar.arrive 2, %0;" ::"n"(FNB_CTA_ROW_THREADS) : "memory");
 }
 __device__ __forceinline__ void distances_ready_wait() {
   __syncwarp();
-  asm volatile("bar.sync 2, %0;" ::"n"(FNB_CTA_THREADS) : "memory");
+  asm volatile("bar.sync 2, %0;" ::"n"(FNB_CTA_ROW_THREADS) : "memory");
 }
 __device__ __forceinline__ void cta_sync() {
   __syncwarp();
   asm volatile("bar.sync 3, %0;" ::"n"(FNB_CTA_THREADS) : "memory");
+}
+//   barrier 4 "candidates published": the driver ARRIVES, the merge warp waits;
+//   barrier 5 "list merged":          the merge warp ARRIVES, the driver waits.           (64 threads each)
+__device__ __forceinline__ void candidates_published_arrive() {
+  __syncwarp();
+  asm volatile("bar.arrive 4, 64;" ::: "memory");
+}
+__device__ __forceinline__ void candidates_published_wait() {
+  __syncwarp();
+  asm volatile("bar.sync 4, 64;" ::: "memory");
+}
+__device__ __forceinline__ void list_merged_arrive() {
+  __syncwarp();
+  asm volatile("bar.arrive 5, 64;" ::: "memory");
+}
+__device__ __forceinline__ void list_merged_wait() {
+  __syncwarp();
+  asm volatile("bar.sync 5, 64;" ::: "memory");
 }
 
 __device__ __forceinline__ uint64_t warp_min_u64(uint64_t v) {
@@ -116,6 +137,10 @@ __global__ void __launch_bounds__(FNB_CTA_WARPS * 32, 2) fnb_search_cta_kernel(c
   uint32_t* ids = tab + p.vs_buckets * 4;                                         // 32 ids
   float* dist = reinterpret_cast<float*>(fnb_smem + p.warp_smem);                 // 32 distances
   volatile uint32_t* ctl = reinterpret_cast<volatile uint32_t*>(dist + 32);       // [0] rows of this round, ~0 = query done
+  // driver <-> merge warp: [1] candidate mask of the round (~0 = query done), [2] list length, [3] pick start hint,
+  // [4] index of the first unexpanded entry (or ~0), and the entry itself / the candidates' keys
+  volatile uint64_t* first_unexp = reinterpret_cast<volatile uint64_t*>(ctl + 8);
+  volatile uint64_t* pend = first_unexp + 1;                                      // 32 keys
   const int pos = lane % G;
   asm volatile("griddepcontrol.launch_dependents;");
 
@@ -125,7 +150,40 @@ __global__ void __launch_bounds__(FNB_CTA_WARPS * 32, 2) fnb_search_cta_kernel(c
     for (int k = 0; k < CH; k++) q[k] = load_query_chunk<DT>(p, qi, (uint32_t)(k * G + pos));
     uint32_t ndist = 0, nhops = 0, len = 0;
 
-    if (warp != 0) {
+    if (warp == FNB_CTA_WARPS - 1) {
+      // ---- merge warp: owns the list between "candidates published" and "list merged" ----
+      for (;;) {
+        candidates_published_wait();
+        const uint32_t am = ctl[1];
+        if (am == 0xffffffffu && ctl[2] == 0xffffffffu) break;
+        uint32_t len = ctl[2], start = ctl[3];
+        const uint64_t key = pend[lane];
+        const bool acc = (am >> lane) & 1u;
+        if (am) merge_accepted(list, len, start, p.B, p.Bpow2, key, acc, lane);
+        // the first unexpanded entry of the merged list, for the driver's pick
+        uint64_t e_list = ~0ull;
+        uint32_t i_list = 0xffffffffu;
+        for (uint32_t base = start & ~31u; base < len; base += 32) {
+          const uint32_t i = base + lane;
+          const uint64_t e = (i < len) ? list[i] : 1ull;
+          const unsigned b = __ballot_sync(FNB_FULL, !(e & 1ull));
+          if (b) {
+            const int src = __ffs(b) - 1;
+            e_list = shfl64(e, src);
+            i_list = base + (uint32_t)src;
+            break;
+          }
+        }
+        __syncwarp();  // every lane has read the control words above
+        if (lane == 0) {
+          ctl[2] = len;
+          ctl[3] = i_list != 0xffffffffu ? i_list : start;
+          ctl[4] = i_list;
+          first_unexp[0] = e_list;
+        }
+        list_merged_arrive();
+      }
+    } else if (warp != 0) {
       // ---- workers: evaluate their quarter of every published round of rows ----
       for (;;) {
         rows_published_wait();
@@ -162,14 +220,25 @@ __global__ void __launch_bounds__(FNB_CTA_WARPS * 32, 2) fnb_search_cta_kernel(c
         }
         len = 1;
         __syncwarp();
-        uint32_t start = 0;
         uint64_t pkey = 0;  // this lane's accepted candidate of the previous round, not merged yet
         bool pacc = false;
+        if (lane == 0) {
+          ctl[2] = 1u;  // list length
+          ctl[3] = 0u;  // pick start hint
+        }
 
         // ---- main loop (Index.h:627-658), software-pipelined: see the header comment ----
         while (cur != FNB_EMPTY) {
           nhops++;
           for (uint32_t l0 = 0; l0 < p.M; l0 += 32) {
+            // hand the previous round's accepted candidates to the merge warp, then start this round
+            pend[lane] = pkey;
+            {
+              const unsigned am = __ballot_sync(FNB_FULL, pacc);
+              if (lane == 0) ctl[1] = am;
+            }
+            candidates_published_arrive();
+            pacc = false;
             uint32_t nb = cur;
             if (l0 + lane < p.M) nb = __ldg(p.adj + (size_t)cur * p.M + l0 + lane);
             const bool fresh = (nb != cur) && visited_test_and_set(tab, p, nb);
@@ -184,33 +253,22 @@ __global__ void __launch_bounds__(FNB_CTA_WARPS * 32, 2) fnb_search_cta_kernel(c
             if (n) {
               if (lane == 0) ctl[0] = n;
               rows_published_arrive();  // the workers start fetching
+              ndist += n;
+              distances_ready_wait();
             }
-            // the previous round's accepted candidates go into the list while this round's rows are in flight
-            if (__any_sync(FNB_FULL, pacc)) merge_accepted(list, len, start, p.B, p.Bpow2, pkey, pacc, lane);
-            pacc = false;
-            if (!n) continue;
-            ndist += n;
-            distances_ready_wait();
-            const bool full = len >= p.B;
-            const uint32_t worst_hi = (uint32_t)(list[len - 1] >> 32);
-            pkey = make_key(fresh ? dist[myrank] : 0.f, nb);
-            pacc = fresh && (!full || (uint32_t)(pkey >> 32) < worst_hi);
+            list_merged_wait();  // the list now holds every earlier round's candidates
+            len = ctl[2];
+            if (n) {
+              const bool full = len >= p.B;
+              const uint32_t worst_hi = (uint32_t)(list[len - 1] >> 32);
+              pkey = make_key(fresh ? dist[myrank] : 0.f, nb);
+              pacc = fresh && (!full || (uint32_t)(pkey >> 32) < worst_hi);
+            }
             __syncwarp();
           }
           // ---- next node: min(first unexpanded list entry, smallest pending candidate) ----
-          uint64_t e_list = ~0ull;
-          uint32_t i_list = 0;
-          for (uint32_t base = start & ~31u; base < len; base += 32) {
-            const uint32_t i = base + lane;
-            const uint64_t e = (i < len) ? list[i] : 1ull;
-            const unsigned b = __ballot_sync(FNB_FULL, !(e & 1ull));
-            if (b) {
-              const int src = __ffs(b) - 1;
-              e_list = shfl64(e, src);
-              i_list = base + (uint32_t)src;
-              break;
-            }
-          }
+          const uint32_t i_list = ctl[4];
+          const uint64_t e_list = i_list != 0xffffffffu ? first_unexp[0] : ~0ull;
           uint64_t kmin;
           for (;;) {
             kmin = warp_min_u64(pacc ? pkey : ~0ull);
@@ -227,15 +285,21 @@ __global__ void __launch_bounds__(FNB_CTA_WARPS * 32, 2) fnb_search_cta_kernel(c
             if (pacc && pkey == kmin) pkey |= 1ull;  // enters the list as expanded (a duplicated link: both copies, one is dropped)
           } else if (e_list != ~0ull) {
             cur = (uint32_t)e_list >> 1;
-            __syncwarp();  // every lane has read its entries of the scan above
-            if (lane == 0) list[i_list] = e_list | 1ull;
-            start = i_list;
+            __syncwarp();
+            if (lane == 0) list[i_list] = e_list | 1ull;  // the merge warp is idle between "list merged" and the next hand-over
             __syncwarp();
           } else {
             cur = FNB_EMPTY;
           }
         }
+        len = ctl[2];
       }
+      __syncwarp();  // every lane has read the list length
+      if (lane == 0) {
+        ctl[1] = 0xffffffffu;
+        ctl[2] = 0xffffffffu;
+      }
+      candidates_published_arrive();  // releases the merge warp from this query
       if (lane == 0) ctl[0] = 0xffffffffu;
       rows_published_arrive();  // releases the workers from this query
 
@@ -288,7 +352,7 @@ cudaError_t launch_search_cta(const SearchParams& p, int num_sms, cudaStream_t s
   const bool exact = p.nchunks == (uint32_t)(G * CH);
   static LaunchCache cache[2][16];
   auto kern = exact ? fnb_search_cta_kernel<DT, METRIC, G, CH, true> : fnb_search_cta_kernel<DT, METRIC, G, CH, false>;
-  const size_t smem = (size_t)p.warp_smem + 32 * 4 + 64;
+  const size_t smem = (size_t)p.warp_smem + 32 * 4 + 32 + 8 + 32 * 8;  // + distances, control words, first unexpanded entry, candidate keys
   int ctas_per_sm = 0;
   cudaError_t e = plan_launch(kern, FNB_CTA_WARPS * 32, smem, cache[exact ? 1 : 0], &ctas_per_sm);
   if (e != cudaSuccess) return e;

@@ -72,8 +72,10 @@ typedef struct fnb_search_stats {
   int64_t n_hops;        /* expanded nodes */
   int64_t n_short;       /* queries with fewer than K results */
   int64_t algo_bytes;    /* n_dist*D*s + n_hops*M*4 + Q*D*s + Q*K*8    */
-  float kernel_ms;       /* device time of the traversal kernel(s), max over devices (CUDA events) */
-  float total_ms;        /* device time incl. host<->device copies (host-buffer entry point only) */
+  float kernel_ms;       /* device time of the traversal kernel(s), max over devices (CUDA events).  Recorded when the
+                            call synchronises its stream anyway, or when FNB_TIME_KERNELS=1 is set in the environment;
+                            0 otherwise (a call that completes by the pinned-memory flag records no events) */
+  float total_ms;        /* device time incl. host<->device copies (host-buffer entry point only); as kernel_ms */
   int32_t kernel_launches;
   int32_t reserved;
 } fnb_search_stats;

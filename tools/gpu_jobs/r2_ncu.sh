@@ -30,5 +30,8 @@ timeout 600 ncu --set full --clock-control none --import-source on -f -k regex:b
 python tools/ncu_summary.py r2_build_prune - /tmp/p_bprune.ncu-rep --name build_prune_kernel --no-traffic
 timeout 600 ncu --set full --clock-control none --import-source on -f -k regex:exchange_merge_kernel -s 2 -c 1 -o /tmp/p_ex python tools/sanitizer_cases.py --child exchange > gpurun_out/r2ncu_ex.log 2>&1
 python tools/ncu_summary.py r2_exchange - /tmp/p_ex.ncu-rep --name exchange_merge_kernel --no-traffic
+# 8. the launches of smoke() (what the driver's GPUTEST lists)
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file /tmp/smoke.csv python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2ncu_smoke.log 2>&1
+python tools/ncu_summary.py r2_smoke /tmp/smoke.csv -
 cp /tmp/p_cfg1.ncu-rep gpurun_out/r2_cfg1_search_kernel.ncu-rep
 ls -la gpurun_out/profiles_r2

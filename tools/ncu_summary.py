@@ -137,5 +137,6 @@ if __name__ == "__main__":
     if sys.argv[2] != "-":
         launches(tag, sys.argv[2])
     shape = sys.argv[sys.argv.index("--shape") + 1] if "--shape" in sys.argv else True
-    full(tag, sys.argv[3], name=name, traffic_json=False if "--no-traffic" in sys.argv else shape)
+    if sys.argv[3] != "-":
+        full(tag, sys.argv[3], name=name, traffic_json=False if "--no-traffic" in sys.argv else shape)
     print("wrote profiles for", tag)
