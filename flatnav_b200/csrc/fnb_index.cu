@@ -698,6 +698,136 @@ int fnb_search_device_totals(fnb_index* ix, int replica, int64_t* n_dist, int64_
   return FNB_OK;
 }
 
+// ---- latency batches of concurrent callers, combined -------------------------------------------------------------
+// A latency batch (a query or a handful, e.g. Index::search from the C++ shim) costs one kernel launch, and the
+// launches of one CUDA context are serialised in the driver: T host threads each launching their own kernel stop
+// scaling at a few tens of thousands of launches per second.  So requests queue on the replica; whoever finds no
+// launch being prepared becomes the collector, takes every waiting request with the same (K, ef_search,
+// num_initializations), copies their queries into one lane's pinned block and launches ONE kernel for all of them; the
+// next collector starts as soon as that launch is issued (several combined launches are in flight at a time), and the
+// collector waits for its kernel (flag in pinned memory), hands every request its results and counters and wakes the
+// callers.  Without contention a request is its own collector at once: nothing is added to a lone caller's path.
+static int run_combined(fnb_index* ix, Replica& r, std::vector<CombReq*>& batch, bool* launched) {
+  const Header& h = ix->h;
+  const int K = batch[0]->K;
+  int64_t total = 0;
+  for (CombReq* c : batch) total += c->nq;
+  SearchParams p;
+  int rc = plan_search(ix, total, K, batch[0]->ef, batch[0]->ninit, &p);
+  if (rc != FNB_OK) return rc;
+  CU(cudaSetDevice(r.device));
+  LaneHold hold;
+  hold.r = &r;
+  rc = acquire_lane(r, &hold.l);
+  if (rc != FNB_OK) return rc;
+  Lane& ln = *hold.l;
+  const size_t qb = (size_t)total * h.data_size, ob = (size_t)total * K * 4, cb = (size_t)total * 4;
+  const size_t off_dist = align256(qb), off_label = off_dist + align256(ob), off_nd = off_label + align256(ob),
+               off_nh = off_nd + align256(cb), off_len = off_nh + align256(cb);
+  rc = ensure_workspace(&ln, 0, off_len + align256(cb));
+  if (rc != FNB_OK) return rc;
+  unsigned char* dp = ln.h_pinned_dev;
+  size_t at = 0;
+  for (CombReq* c : batch) {
+    memcpy(ln.h_pinned + at * h.data_size, c->q, (size_t)c->nq * h.data_size);
+    at += (size_t)c->nq;
+  }
+  p.vec = r.vec;
+  p.adj = r.adj;
+  p.labels = r.labels;
+  p.queries = dp;
+  p.out_dist = reinterpret_cast<float*>(dp + off_dist);
+  p.out_label = reinterpret_cast<int32_t*>(dp + off_label);
+  p.out_ndist = reinterpret_cast<uint32_t*>(dp + off_nd);
+  p.out_nhops = reinterpret_cast<uint32_t*>(dp + off_nh);
+  p.out_len = reinterpret_cast<uint32_t*>(dp + off_len);
+  p.done = ln.counter + FNB_SLOT_DONE / 4;
+  p.done_seq = ln.h_flag_dev;
+  p.seq = ++ln.seq ? ln.seq : ++ln.seq;
+  cudaError_t e = dispatch_search(ix, p, r.num_sms, ln.stream);
+  if (e != cudaSuccess) return fail(FNB_ERR_CUDA, "search kernel launch failed: %s", cudaGetErrorString(e));
+  // the launch is issued: let the next collector go while this one waits for its kernel
+  {
+    std::lock_guard<std::mutex> lk(r.pool->cmu);
+    r.pool->claunching = false;
+    *launched = true;
+  }
+  r.pool->ccv.notify_all();
+  const auto t0 = std::chrono::steady_clock::now();
+  for (uint32_t spins = 0; *ln.h_flag != p.seq; spins++) {
+    if (spins < 256u) {
+#if defined(__x86_64__) || defined(__i386__)
+      __builtin_ia32_pause();
+#endif
+      continue;
+    }
+    std::this_thread::yield();
+    if ((spins & 1023u) == 0u && std::chrono::steady_clock::now() - t0 > std::chrono::seconds(2)) {
+      CU(cudaStreamSynchronize(ln.stream));
+      break;
+    }
+  }
+  std::atomic_thread_fence(std::memory_order_acquire);
+  hold.drained = true;
+  const uint32_t* c_nd = reinterpret_cast<const uint32_t*>(ln.h_pinned + off_nd);
+  const uint32_t* c_nh = reinterpret_cast<const uint32_t*>(ln.h_pinned + off_nh);
+  const uint32_t* c_len = reinterpret_cast<const uint32_t*>(ln.h_pinned + off_len);
+  at = 0;
+  for (CombReq* c : batch) {
+    memcpy(c->out_dist, ln.h_pinned + off_dist + at * K * 4, (size_t)c->nq * K * 4);
+    memcpy(c->out_label, ln.h_pinned + off_label + at * K * 4, (size_t)c->nq * K * 4);
+    for (int64_t i = 0; i < c->nq; i++) {
+      c->nd += c_nd[at + i];
+      c->nh += c_nh[at + i];
+      c->ns += c_len[at + i] < (uint32_t)K ? 1 : 0;
+    }
+    at += (size_t)c->nq;
+  }
+  return FNB_OK;
+}
+
+static int search_latency_combined(fnb_index* ix, Replica& r, CombReq& me) {
+  LanePool& P = *r.pool;
+  const int64_t cap = 4ll * r.num_sms;  // a combined batch stays a latency batch
+  std::unique_lock<std::mutex> lk(P.cmu);
+  P.cpending.push_back(&me);
+  P.ccv.wait(lk, [&] { return me.taken || !P.claunching; });
+  if (me.taken) {  // somebody's launch carries this request
+    P.ccv.wait(lk, [&] { return me.done; });
+    return me.rc;
+  }
+  // collector: this request and every compatible one that is waiting
+  P.claunching = true;
+  std::vector<CombReq*> batch;
+  int64_t total = 0;
+  for (size_t i = 0; i < P.cpending.size();) {
+    CombReq* c = P.cpending[i];
+    const bool mine = c == &me;
+    if ((mine || (c->K == me.K && c->ef == me.ef && c->ninit == me.ninit)) && (mine || total + c->nq + me.nq <= cap)) {
+      c->taken = true;
+      batch.push_back(c);
+      total += c->nq;
+      P.cpending.erase(P.cpending.begin() + (long)i);
+    } else {
+      i++;
+    }
+  }
+  lk.unlock();
+  bool launched = false;
+  const int rc = run_combined(ix, r, batch, &launched);
+  const std::string err = rc != FNB_OK ? g_last_error : std::string();
+  lk.lock();
+  if (!launched) P.claunching = false;  // failed before the launch was issued
+  for (CombReq* c : batch) {
+    c->rc = rc;
+    c->err = err;
+    c->done = true;
+  }
+  lk.unlock();
+  P.ccv.notify_all();
+  return me.rc;
+}
+
 // Host-buffer search.  Per replica the call takes a lane (stream + counters + staging) from the replica's pool, so
 // concurrent callers proceed side by side.  Three ways for the bytes to travel, chosen per call:
 //   * caller buffers are page-locked (cudaHostAlloc / cudaHostRegister, e.g. torch pinned tensors): used in place — the
@@ -722,6 +852,37 @@ int fnb_search(fnb_index* ix, const void* queries, int64_t Q, int K, int ef_sear
   const Header& h = ix->h;
   const int R = (int)ix->replicas.size();
   DeviceScope scope;
+  static const bool no_combine = getenv("FNB_NO_COMBINE") != nullptr || getenv("FNB_NO_STAGING") != nullptr ||
+                                 getenv("FNB_NO_FLAG_WAIT") != nullptr || getenv("FNB_TIME_KERNELS") != nullptr;
+  if (p0.lat && R == 1 && !no_combine) {
+    CombReq me;
+    me.q = static_cast<const unsigned char*>(queries);
+    me.nq = Q;
+    me.K = K;
+    me.ef = ef_search;
+    me.ninit = num_initializations;
+    me.out_dist = out_dist;
+    me.out_label = out_label;
+    rc = search_latency_combined(ix, ix->replicas[0], me);
+    if (rc != FNB_OK) {
+      g_last_error = me.err;
+      return rc;
+    }
+    if (stats) {
+      stats->n_queries = Q;
+      stats->n_dist = me.nd;
+      stats->n_hops = me.nh;
+      stats->n_short = me.ns;
+      stats->algo_bytes = me.nd * (int64_t)h.data_size + me.nh * (int64_t)h.M * 4 + Q * (int64_t)h.data_size + Q * (int64_t)K * 8;
+      stats->kernel_launches = 1;
+    }
+    if (me.ns > 0) {
+      fail(FNB_SHORT_RESULT, "Search did not return the expected number of results for %lld of %lld queries.",
+           (long long)me.ns, (long long)Q);
+      return FNB_SHORT_RESULT;
+    }
+    return FNB_OK;
+  }
   static const bool no_zero_copy = getenv("FNB_NO_ZEROCOPY") != nullptr;
   static const bool no_staging = getenv("FNB_NO_STAGING") != nullptr;
   static const bool no_feed = getenv("FNB_NO_FEED") != nullptr;
@@ -882,11 +1043,12 @@ int fnb_search(fnb_index* ix, const void* queries, int64_t Q, int K, int ef_sear
     Lane& ln = *held[i].l;
     CU(cudaSetDevice(r.device));
     if (pt.by_flag) {
-      // spin on the pinned word; after a while let other threads of an oversubscribed host run; after 2 s fall back to
-      // the stream (a failed launch never writes the flag: the synchronise reports the error)
+      // spin on the pinned word; after ~10 us offer the core to whoever else wants it on every turn (many callers
+      // spinning on all cores of the host must not starve each other's launch paths); after 2 s fall back to the stream
+      // (a failed launch never writes the flag: the synchronise reports the error)
       const auto t0 = std::chrono::steady_clock::now();
       for (uint32_t spins = 0; *ln.h_flag != pt.seq; spins++) {
-        if (spins < 4096u) {
+        if (spins < 256u) {
 #if defined(__x86_64__) || defined(__i386__)
           __builtin_ia32_pause();
 #endif

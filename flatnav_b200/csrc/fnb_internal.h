@@ -57,6 +57,19 @@ struct Lane {
 #define FNB_SLOT_TOTALS 8       /* u64 x 3  n_dist, n_hops, short results (accumulated with atomics) */
 #define FNB_SLOT_LAST_TOTALS 32 /* u64 x 3  the totals of the launch that used the slot last (read by the host) */
 
+// One caller's share of a combined latency launch.
+struct CombReq {
+  const unsigned char* q = nullptr;
+  int64_t nq = 0;
+  int K = 0, ef = 0, ninit = 0;
+  float* out_dist = nullptr;
+  int32_t* out_label = nullptr;
+  int64_t nd = 0, nh = 0, ns = 0;
+  int rc = 0;
+  std::string err;
+  bool taken = false, done = false;
+};
+
 struct LanePool {
   std::mutex mu;
   std::condition_variable cv;
@@ -66,6 +79,12 @@ struct LanePool {
   std::atomic<uint32_t> ring_seq{0};
   volatile unsigned int* h_done_seq = nullptr;  // pinned: sequence number of the last fnb_search_device launch that finished
   unsigned int* d_done_seq = nullptr;           // its device-side alias
+  // Combining of concurrent latency batches (fnb_search from many host threads): requests queue here; whoever finds
+  // no launch being prepared takes every compatible request waiting and launches them as ONE kernel.
+  std::mutex cmu;
+  std::condition_variable ccv;
+  std::vector<struct CombReq*> cpending;
+  bool claunching = false;
 };
 
 // One full copy of the index in the HBM of one device, plus the per-device launch state.
