@@ -35,6 +35,31 @@ namespace fnb {
 // shared memory beyond SearchParams::warp_smem (see the carve-up in the kernel)
 #define FNB_SPEC_EXTRA_SMEM 2048u
 
+// Development build (-DFNB_SPEC_DEBUG, tools/spec_probe.py): the driver counts events and clock cycles of its waits, and
+// out_ndist receives counter SearchParams::dbg - 1 instead of n_dist.  Not compiled into the shipped library.
+#ifdef FNB_SPEC_DEBUG
+#define FNB_DBG(...) __VA_ARGS__
+// segment i of the hop ends here: its cycles go to counter 4 + i if the hop is of the class asked for
+#define FNB_SEG(i)                      \
+  {                                     \
+    const uint32_t now = clock();       \
+    if (dbg_on) dbgc[4 + (i)] += now - dbg_t; \
+    dbg_t = clock();                    \
+  }
+#define FNB_DBG_END                                                        \
+  dbgc[15] = clock() - dbg_t_loop;                                         \
+  dbgc[0] = nhops;                                                         \
+  if (p.dbg & 0xffu) {                                                     \
+    uint32_t v = 0;                                                        \
+    _Pragma("unroll") for (int i = 0; i < 16; i++) if ((p.dbg & 0xffu) == (uint32_t)i + 1u) v = dbgc[i]; \
+    ndist = v;                                                             \
+  }
+#else
+#define FNB_DBG(...)
+#define FNB_SEG(i)
+#define FNB_DBG_END
+#endif
+
 __host__ __device__ constexpr int fnb_spec_batches(int g, int ch) {
   const int want = FNB_SPEC_ROWS / (32 / g) / FNB_CTA_WORKERS < 1 ? 1 : FNB_SPEC_ROWS / (32 / g) / FNB_CTA_WORKERS;
   const int cap = (g == 32 ? 16 : 24) / ch < 1 ? 1 : (g == 32 ? 16 : 24) / ch;
@@ -200,10 +225,13 @@ __global__ void __launch_bounds__(FNB_CTA_WARPS * 32, 2) fnb_search_cta_spec_ker
         uint32_t round = 0;                                // rounds posted in the main loop
         uint32_t t_node = FNB_EMPTY, t_link = FNB_EMPTY;  // target whose links are loaded (this lane's link) but not posted yet
         uint32_t x_node = FNB_EMPTY, x_link = FNB_EMPTY;  // the best new candidate's links, loaded while the pick is decided
+        FNB_DBG(uint32_t dbgc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; const uint32_t dbg_t_loop = clock();
+                uint32_t dbg_t = 0; bool dbg_on = false; const uint32_t dbg_cls = p.dbg >> 8;)
 
         // ---- main loop (Index.h:627-658), software-pipelined as in fnb_search_cta_kernel ----
         while (cur != FNB_EMPTY) {
           nhops++;
+          FNB_DBG(dbg_t = clock(); dbg_on = false; uint32_t dbg_a = 0;)
           for (uint32_t l0 = 0; l0 < p.M; l0 += 32) {
             // hand the previous round's accepted candidates to the merge warp, then start this round
             pend[lane] = pkey;
@@ -213,6 +241,7 @@ __global__ void __launch_bounds__(FNB_CTA_WARPS * 32, 2) fnb_search_cta_spec_ker
             }
             candidates_published_arrive();
             pacc = false;
+            FNB_DBG(dbg_a = clock() - dbg_t; dbg_t = clock();)
 
             // -- the node's links: a slot (with distances), a target not posted yet, the early load of the pick, or memory
             uint32_t nb = cur, vm = 0;
@@ -241,6 +270,9 @@ __global__ void __launch_bounds__(FNB_CTA_WARPS * 32, 2) fnb_search_cta_spec_ker
             } else if (l0 + lane < p.M) {
               nb = __ldg(p.adj + (size_t)cur * p.M + l0 + lane);
             }
+            FNB_DBG(dbg_on = dbg_cls == 0u || (dbg_cls == 1u && s >= 0) || (dbg_cls == 2u && s < 0); if (dbg_on) dbgc[4] += dbg_a;
+                    if (s >= 0) dbgc[1]++;)
+            FNB_SEG(1)
             const bool fresh = (nb != cur) && visited_test_and_set(tab, p, nb);
             const bool have = fresh && ((vm >> lane) & 1u);
             const bool need = fresh && !have;
@@ -252,16 +284,19 @@ __global__ void __launch_bounds__(FNB_CTA_WARPS * 32, 2) fnb_search_cta_spec_ker
               const uint32_t* arow = p.adj + (size_t)nb * p.M;  // whichever of them is expanded later finds its links in L2
               for (uint32_t o = 0; o < p.M; o += 32) prefetch_l2(arow + o);
             }
+            FNB_SEG(2)
             // -- the target whose links were loaded during the previous hop: rows of its unvisited links join this round
             const bool postB = (l0 == 0) && (t_node != FNB_EMPTY);
             const bool bfresh = postB && (t_link != t_node) && !visited_peek(tab, p, t_link);
             const unsigned bm = __ballot_sync(FNB_FULL, bfresh);
             const uint32_t nB = (uint32_t)__popc(bm);
+            FNB_SEG(3)
             if (postB || nA) {
               if ((nA + nB) && outstanding) {  // one round in flight at a time: rows[] / dst[] are the workers' until they are done
                 distances_ready_wait();
                 outstanding = false;
               }
+              FNB_SEG(4)
               uint32_t sB = 0;
               if (postB) {
                 // a free slot, else the one filled longest ago
@@ -290,16 +325,20 @@ __global__ void __launch_bounds__(FNB_CTA_WARPS * 32, 2) fnb_search_cta_spec_ker
                 rows_published_arrive();  // the workers start fetching
                 outstanding = true;
                 round++;
+                FNB_DBG(dbgc[2]++; dbgc[3] += nA + nB;)
               }
               if (postB) t_node = FNB_EMPTY;
             }
             ndist += n;
+            FNB_SEG(5)
             if (nA) {  // the hop waits for its own rows only
               distances_ready_wait();
               outstanding = false;
             }
+            FNB_SEG(6)
             list_merged_wait();  // the list now holds every earlier round's candidates
             len = ctl[2];
+            FNB_SEG(7)
             // -- next target: the first leading unexpanded entry that has no slot yet; its links are loaded now, used a hop later
             if (l0 + 32 >= p.M && t_node == FNB_EMPTY) {
 #pragma unroll
@@ -311,6 +350,7 @@ __global__ void __launch_bounds__(FNB_CTA_WARPS * 32, 2) fnb_search_cta_spec_ker
               }
               if (t_node != FNB_EMPTY) t_link = (uint32_t)lane < p.M ? __ldg(p.adj + (size_t)t_node * p.M + lane) : t_node;
             }
+            FNB_SEG(8)
             if (n) {
               const bool full = len >= p.B;
               const uint32_t worst_hi = (uint32_t)(list[len - 1] >> 32);
@@ -319,6 +359,7 @@ __global__ void __launch_bounds__(FNB_CTA_WARPS * 32, 2) fnb_search_cta_spec_ker
               pacc = fresh && (!full || (uint32_t)(pkey >> 32) < worst_hi);
             }
             __syncwarp();
+            FNB_SEG(9)
           }
           // ---- next node: min(first unexpanded list entry, smallest pending candidate) ----
           const uint32_t i_list = ctl[4];
@@ -350,8 +391,10 @@ __global__ void __launch_bounds__(FNB_CTA_WARPS * 32, 2) fnb_search_cta_spec_ker
           } else {
             cur = FNB_EMPTY;
           }
+          FNB_SEG(10)
         }
         len = ctl[2];
+        FNB_DBG_END
       }
       if (outstanding) {  // a round of target rows nobody needs any more: still collected, once per round
         distances_ready_wait();

@@ -100,6 +100,8 @@ struct SearchParams {
   uint32_t query_pitch_chunks;  // != 0 => queries are rows of a padded vector array with this pitch (construction:
                                 // the new nodes' own rows); chunks beyond the data are zero there
   uint32_t dense;  // 1 => the 28-warps-per-SM instantiation (large batches of short rows; never with lat)
+  uint32_t pf2;  // CTA latency kernel: two-hop prefetch (see cta_rows); set by the host for batches of a few queries
+  uint32_t dbg;  // development builds only (-DFNB_SPEC_DEBUG): which counter of the speculating latency kernel replaces n_dist
   uint32_t lat;  // latency variants (few queries; query = blockIdx.x, grid-stride, `counter` unused): 1 => one warp per
                  // CTA (fnb_search_kernel<.., LAT>), 2 => one CTA of six warps per query (search_cta_kernel.cuh), 3 => the same with
                  // speculative row evaluation (search_cta_spec_kernel.cuh)
@@ -862,15 +864,15 @@ inline uint32_t choose_dense_plan(int64_t Q, int num_sms, int lanes_per_row, int
 }
 
 // Host rule for SearchParams::lat: a latency variant when every query of the batch can have an SM quarter of its own
-// (<= 4 CTAs per SM): the CTA-per-query kernel with speculative row evaluation (3).  FNB_LAT=0 / 1 / 2 / 3 forces the
-// throughput kernel / the one-warp latency variant / the plain CTA kernel / the speculating one (tests, experiments).
+// (<= 4 CTAs per SM): the CTA-per-query kernel (2).  FNB_LAT=0 / 1 / 2 / 3 forces the throughput kernel / the one-warp
+// latency variant / the CTA kernel / the CTA kernel with speculative row evaluation (tests, experiments).
 inline uint32_t choose_latency_variant(int64_t Q, int num_sms) {
   static const int forced = [] {
     const char* e = getenv("FNB_LAT");
     return e ? atoi(e) : -1;
   }();
   if (forced >= 0) return forced > 3 ? 3u : (uint32_t)forced;
-  return Q <= 4ll * num_sms ? 3u : 0u;
+  return Q <= 4ll * num_sms ? 2u : 0u;
 }
 
 }  // namespace fnb
