@@ -411,23 +411,13 @@ int plan_search(const fnb_index* ix, int64_t Q, int K, int ef, int ninit, Search
   const int sms = ix->replicas.empty() ? 148 : ix->replicas[0].num_sms;
   if (launch_q <= 0) launch_q = Q;
   p->lat = allow_latency_variant ? choose_latency_variant(launch_q, sms) : 0u;
-#ifdef FNB_SPEC_DEBUG
-  if (const char* d = getenv("FNB_SPEC_STATS")) p->dbg = (uint32_t)atoi(d);
-#endif
-  // Two-hop prefetch of the CTA latency kernel: ~16 KB of extra L2 fills per accepted candidate, free while the batch
-  // leaves the memory system idle (FNB_PF2_MAXQ, default 64 queries per launch; 0 disables).
-  static const long long pf2_maxq = [] {
-    const char* e = getenv("FNB_PF2_MAXQ");
-    return e ? atoll(e) : 64ll;
-  }();
-  p->pf2 = (p->lat == 2u && launch_q <= pf2_maxq && h.M % 4 == 0) ? 1u : 0u;
   p->dense = p->lat ? 0u : choose_dense_plan(launch_q, sms, ix->G, cpl, p->B);
-  if (p->lat >= 2u)  // one query per CTA, up to 4 CTAs per SM: the visited set can have its full size
-    size_visited(*p, env ? atoi(env) : 0, 4, 1, p->lat == 3u ? 1024u + FNB_SPEC_EXTRA_SMEM : 1024u);
+  if (p->lat == 2u)  // one query per CTA, up to 4 CTAs per SM: the visited set can have its full size
+    size_visited(*p, env ? atoi(env) : 0, 4, 1);
   else
     size_visited(*p, env ? atoi(env) : 0, p->dense ? FNB_CTAS_DENSE : fnb_min_ctas(cpl));
   const uint32_t queries_per_cta = p->lat ? 1u : (uint32_t)FNB_WARPS_PER_CTA;
-  if ((uint64_t)p->warp_smem * queries_per_cta + 1024u + (p->lat == 3u ? FNB_SPEC_EXTRA_SMEM : 0u) > 227u * 1024u)
+  if ((uint64_t)p->warp_smem * queries_per_cta + 1024u > 227u * 1024u)
     return fail(FNB_ERR_UNSUPPORTED, "ef_search=%d needs %u bytes of shared memory per query; limit is %u", ef,
                 p->warp_smem, 226u * 1024u / queries_per_cta);
   return FNB_OK;
@@ -660,9 +650,8 @@ int fnb_search_kernel_signature(const fnb_index* ix, int64_t Q, int K, int ef_se
   const int dt = ix->h.data_type == FNB_DTYPE_FLOAT32 ? DT_F32 : (ix->h.data_type == FNB_DTYPE_UINT8 ? DT_U8 : DT_I8);
   const int exact = p.nchunks == (uint32_t)(ix->G * CH) ? 1 : 0;
   const int occ = (!lat && p.dense && CH <= 4 && ix->G <= 8) ? FNB_CTAS_DENSE : 0;
-  if (lat >= 2)
-    snprintf(out, cap, "fnb_search_cta%s_kernel<%d,%d,%d,%d,%d>", lat == 3 ? "_spec" : "", dt,
-             ix->h.metric == FNB_METRIC_IP ? M_IP : M_L2, ix->G, CH, exact);
+  if (lat == 2)
+    snprintf(out, cap, "fnb_search_cta_kernel<%d,%d,%d,%d,%d>", dt, ix->h.metric == FNB_METRIC_IP ? M_IP : M_L2, ix->G, CH, exact);
   else
     snprintf(out, cap, "fnb_search_kernel<%d,%d,%d,%d,%d,%d,%d>", dt, ix->h.metric == FNB_METRIC_IP ? M_IP : M_L2, ix->G,
              CH, exact, lat, occ);
@@ -683,11 +672,11 @@ int fnb_search_plan(const fnb_index* ix, int64_t Q, int K, int ef_search, fnb_pl
   out->list_capacity = (int32_t)p.Bcap;
   out->visited_slots = (int32_t)(p.vs_buckets * (p.vs_wide ? 4u : 8u));
   out->smem_bytes_per_query = (int32_t)p.warp_smem;
-  const int by_regs = out->latency_variant >= 2 ? 4 : (out->latency_variant ? 8 : (p.dense ? FNB_CTAS_DENSE : fnb_min_ctas(cpl)));
+  const int by_regs = out->latency_variant == 2 ? 4 : (out->latency_variant ? 8 : (p.dense ? FNB_CTAS_DENSE : fnb_min_ctas(cpl)));
   const int queries_per_cta = out->latency_variant ? 1 : FNB_WARPS_PER_CTA;
-  const int by_smem = (int)((227u * 1024u) / ((uint32_t)p.warp_smem * queries_per_cta + 1024u + (p.lat == 3u ? FNB_SPEC_EXTRA_SMEM : 0u)));
+  const int by_smem = (int)((227u * 1024u) / ((uint32_t)p.warp_smem * queries_per_cta + 1024u));
   out->ctas_per_sm = std::min(by_regs, by_smem);
-  out->warps_per_sm = out->ctas_per_sm * (out->latency_variant >= 2 ? FNB_CTA_WARPS : (out->latency_variant ? 1 : FNB_WARPS_PER_CTA));
+  out->warps_per_sm = out->ctas_per_sm * (out->latency_variant == 2 ? FNB_CTA_WARPS : (out->latency_variant ? 1 : FNB_WARPS_PER_CTA));
   out->queries_per_sm = out->ctas_per_sm * queries_per_cta;
   return FNB_OK;
 }

@@ -11,7 +11,7 @@
 #include <vector>
 
 #include "fnb_layout.h"
-#include "search_cta_spec_kernel.cuh"
+#include "search_cta_kernel.cuh"
 #include "search_kernel.cuh"
 
 #define FNB_HEADER_BYTES 60u
@@ -153,7 +153,6 @@ cudaError_t dispatch_search_i8(const fnb_index* ix, const SearchParams& p, int n
 
 template <int DT, int METRIC, int G, int CH>
 static inline cudaError_t launch_any(const SearchParams& p, int num_sms, cudaStream_t s) {
-  if (p.lat == 3u) return launch_search_cta_spec<DT, METRIC, G, CH>(p, num_sms, s);
   return p.lat == 2u ? launch_search_cta<DT, METRIC, G, CH>(p, num_sms, s) : launch_search<DT, METRIC, G, CH>(p, num_sms, s);
 }
 

@@ -100,11 +100,8 @@ struct SearchParams {
   uint32_t query_pitch_chunks;  // != 0 => queries are rows of a padded vector array with this pitch (construction:
                                 // the new nodes' own rows); chunks beyond the data are zero there
   uint32_t dense;  // 1 => the 28-warps-per-SM instantiation (large batches of short rows; never with lat)
-  uint32_t pf2;  // CTA latency kernel: two-hop prefetch (see cta_rows); set by the host for batches of a few queries
-  uint32_t dbg;  // development builds only (-DFNB_SPEC_DEBUG): which counter of the speculating latency kernel replaces n_dist
   uint32_t lat;  // latency variants (few queries; query = blockIdx.x, grid-stride, `counter` unused): 1 => one warp per
-                 // CTA (fnb_search_kernel<.., LAT>), 2 => one CTA of six warps per query (search_cta_kernel.cuh), 3 => the same with
-                 // speculative row evaluation (search_cta_spec_kernel.cuh)
+                 // CTA (fnb_search_kernel<.., LAT>), 2 => one CTA of four warps per query (search_cta_kernel.cuh)
   // Self-cleaning launch state (fnb_search_device): != null => the last warp of the grid to finish copies `totals` to
   // `last_totals`, zeroes counter / totals / done for the slot's next user and reports `seq` to the host — no memset
   // between launches, so consecutive launches are adjacent in the stream and can overlap (pdl).
@@ -718,8 +715,7 @@ __global__ void __launch_bounds__(LAT ? 32 : FNB_WARPS_PER_CTA * 32, LAT ? 1 : (
 // Shared memory per warp = list (Bcap*8) + visited set (buckets*16) + 128 B scratch.  The visited set takes what
 // the planned occupancy (min_ctas CTAs of 4 warps per SM) leaves of the 227 KB, up to ~48 slots per list entry
 // (~20 evaluations per unit of ef were measured on the BASELINE configs, so <= 45 % load).
-inline void size_visited(SearchParams& p, int force_buckets, int min_ctas, int queries_per_cta = FNB_WARPS_PER_CTA,
-                         uint32_t cta_overhead = 1024u) {
+inline void size_visited(SearchParams& p, int force_buckets, int min_ctas, int queries_per_cta = FNB_WARPS_PER_CTA) {
   const uint32_t list_bytes = p.Bcap * 8u + 128u;
   uint32_t nbits = 1;
   while ((1ull << nbits) < (uint64_t)p.N && nbits < 31) nbits++;
@@ -743,7 +739,7 @@ inline void size_visited(SearchParams& p, int force_buckets, int min_ctas, int q
     const uint32_t floor_b = p.B / 8u > 16u ? p.B / 8u : 16u;
     buckets = 16u;
     for (int c = min_ctas; c >= 1; c--) {
-      const uint32_t budget = (227u * 1024u - (uint32_t)c * cta_overhead) / ((uint32_t)c * (uint32_t)queries_per_cta);  // per query
+      const uint32_t budget = (227u * 1024u - (uint32_t)c * 1024u) / ((uint32_t)c * (uint32_t)queries_per_cta);  // per query
       const uint32_t room = budget > list_bytes ? (budget - list_bytes) / 16u : 0u;
       buckets = want < room ? want : room;
       if (buckets >= floor_b || c == 1) break;
@@ -864,14 +860,14 @@ inline uint32_t choose_dense_plan(int64_t Q, int num_sms, int lanes_per_row, int
 }
 
 // Host rule for SearchParams::lat: a latency variant when every query of the batch can have an SM quarter of its own
-// (<= 4 CTAs per SM): the CTA-per-query kernel (2).  FNB_LAT=0 / 1 / 2 / 3 forces the throughput kernel / the one-warp
-// latency variant / the CTA kernel / the CTA kernel with speculative row evaluation (tests, experiments).
+// (<= 4 CTAs per SM): the CTA-per-query kernel (2).  FNB_LAT=0 / 1 / 2 forces the throughput kernel / the one-warp
+// latency variant / the CTA kernel (tests, experiments).
 inline uint32_t choose_latency_variant(int64_t Q, int num_sms) {
   static const int forced = [] {
     const char* e = getenv("FNB_LAT");
     return e ? atoi(e) : -1;
   }();
-  if (forced >= 0) return forced > 3 ? 3u : (uint32_t)forced;
+  if (forced >= 0) return forced > 2 ? 2u : (uint32_t)forced;
   return Q <= 4ll * num_sms ? 2u : 0u;
 }
 

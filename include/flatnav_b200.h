@@ -196,7 +196,7 @@ int fnb_search_kernel_signature(const fnb_index* index, int64_t Q, int K, int ef
 
 /* Measurement aid: the launch plan of a search of this shape (what bounds the resident queries per SM). */
 typedef struct fnb_plan_info {
-  int32_t latency_variant;      /* batches of at most 4 x SMs queries: 2 = one CTA of six warps per query (default),
+  int32_t latency_variant;      /* batches of at most 4 x SMs queries: 2 = one CTA of four warps per query (default),
                                    1 = one warp per CTA; 0 = throughput kernel (one warp per query, 4 per CTA) */
   int32_t dense_plan;           /* 1: the 28-warps-per-SM instantiation (large batches of rows up to 512 B) */
   int32_t list_capacity;        /* max(ef_search, K) rounded up to 32 entries of 8 bytes */

@@ -4,7 +4,7 @@ variant, construction, re-rank, brute force and the exchange kernel on inputs sm
 
     compute-sanitizer --tool memcheck python tools/sanitizer_cases.py [variant ...]
 
-Variants: spec (default latency kernel: CTA per query with speculative row evaluation), cta (the plain CTA kernel), lat1 (one-warp latency variant), thr (throughput kernel, 24-warp plan),
+Variants: cta (default latency kernel), lat1 (one-warp latency variant), thr (throughput kernel, 24-warp plan),
 dense (28-warp plan), fed (pageable batch fed to the running kernel), build, rerank, brute, exchange.
 Each search result is compared with the golden output of the same call made earlier WITHOUT the sanitizer
 (tests/golden), so the run is also a parity check.
@@ -17,7 +17,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-ENV = {"spec": {"FNB_LAT": "3"}, "cta": {"FNB_LAT": "2"}, "lat1": {"FNB_LAT": "1"}, "thr": {"FNB_LAT": "0", "FNB_DENSE": "0"},
+ENV = {"cta": {"FNB_LAT": "2"}, "lat1": {"FNB_LAT": "1"}, "thr": {"FNB_LAT": "0", "FNB_DENSE": "0"},
        "dense": {"FNB_LAT": "0", "FNB_DENSE": "1"}, "fed": {"FNB_LAT": "0"}}
 
 
@@ -31,7 +31,7 @@ def child(variant: str) -> None:
     gold = os.path.join(ROOT, "tests", "golden")
     cases = json.load(open(os.path.join(gold, "golden.json")))
     DT = {"f32": DataType.float32, "u8": DataType.uint8, "i8": DataType.int8}
-    if variant in ("spec", "cta", "lat1", "thr", "dense"):
+    if variant in ("cta", "lat1", "thr", "dense"):
         for case in cases[:4]:
             g = np.load(os.path.join(gold, case["name"] + ".npz"))
             cls = flatnav_b200.index.index_class("l2" if case["metric"] == "l2" else "angular", DT[case["dtype"]])
@@ -104,7 +104,7 @@ def main() -> None:
     if len(sys.argv) > 2 and sys.argv[1] == "--child":
         child(sys.argv[2])
         return
-    variants = sys.argv[1:] or ["spec", "cta", "lat1", "thr", "dense", "fed", "build", "rerank", "brute", "exchange"]
+    variants = sys.argv[1:] or ["cta", "lat1", "thr", "dense", "fed", "build", "rerank", "brute", "exchange"]
     rc = 0
     for v in variants:  # one process per variant: the environment knobs are read once per process
         r = subprocess.run([sys.executable, os.path.abspath(__file__), "--child", v], env=dict(os.environ, **ENV.get(v, {})))
