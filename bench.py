@@ -20,6 +20,8 @@ Numbers:
   e2e       the same metric through the public host-buffer API (flatnav_b200 ... .search(numpy) ->
             fnb_search): pinned host queries -> H2D -> kernel -> D2H results, every step.
   e2e_pageable  the same call with what a reference-binding caller passes: ordinary (pageable) numpy in, fresh numpy out.
+  e2e_two_callers  the e2e call made by two host threads on alternate steps, each on its own pinned buffers (the engine is
+            re-entrant: one caller's launch fills the tail of the other's).  Reported beside e2e, never instead of it.
   roofline  HBM bound. achieved = algorithmic bytes per launch / mean kernel duration (per-launch CUDA
             events recorded inside the timed region); algorithmic bytes = n_dist*D*s + n_hops*M*4 + Q*D*s
             + Q*K*8 with n_dist / n_hops counted by the kernel.  peak = MEASURED_PEAKS.json
