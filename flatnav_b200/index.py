@@ -20,6 +20,18 @@ from .data_type import DataType
 
 _NP = {DataType.float32: np.float32, DataType.uint8: np.uint8, DataType.int8: np.int8}
 
+_from_buffer = C.c_char.from_buffer
+_addressof = C.addressof
+
+
+def _ptr(a: np.ndarray) -> int:
+    """Address of a C-contiguous array's data.  `ndarray.ctypes.data` builds a helper object on every access (~1.9 us,
+    three of them per search call: as much as everything else the wrapper does for one query); the buffer protocol gives
+    the address in ~0.3 us, for writable non-empty arrays."""
+    if a.size and a.flags.writeable:
+        return _addressof(_from_buffer(a))
+    return a.ctypes.data
+
 
 class _GpuIndex:
     _metric: int = _capi.FNB_METRIC_L2
@@ -35,7 +47,12 @@ class _GpuIndex:
         self._num_threads = max(1, (os.cpu_count() or 1) // 2)
         self._n_dist = 0
         self._label_id = 0  # PyIndex::_label_id (bindings.cpp:232): labels handed out by allocate_nodes
-        self.last_stats: dict = {}
+        self._last_st = None  # FnbSearchStats of the last search call
+
+    @property
+    def last_stats(self) -> dict:
+        """Counters of the last `search` / `search_single` call (n_queries, n_dist, n_hops, kernel_ms, ...)."""
+        return self._last_st.as_dict() if self._last_st is not None else {}
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
@@ -111,9 +128,9 @@ class _GpuIndex:
             dist = np.empty((Q, K), dtype=np.float32)
             lab = np.empty((Q, K), dtype=np.int32)
         st = _capi.FnbSearchStats()
-        rc = _capi.lib().fnb_search(self._h, q.ctypes.data, Q, int(K), int(ef_search), int(num_initializations),
-                                    dist.ctypes.data, lab.ctypes.data, C.byref(st))
-        self.last_stats = st.as_dict()
+        rc = _capi.lib().fnb_search(self._h, _ptr(q), Q, int(K), int(ef_search), int(num_initializations),
+                                    _ptr(dist), _ptr(lab), C.byref(st))
+        self._last_st = st
         self._n_dist += int(st.n_dist)
         _capi.check(rc)
         return dist, lab
