@@ -132,3 +132,20 @@ def test_hostile_headers_are_rejected_before_any_allocation(kw):
     rc = _capi.lib().fnb_index_from_memory(blob, len(blob), _capi.FNB_METRIC_L2, _capi.FNB_DTYPE_ANY, None, 0, C.byref(out))
     assert rc in (_capi.FNB_ERR_FORMAT, _capi.FNB_ERR_UNSUPPORTED), (rc, _capi.last_error())
     assert not out.value
+
+
+def test_array_address_helper_matches_numpy():
+    """index._ptr (buffer-protocol fast path of the search wrapper) gives the address ndarray.ctypes.data gives, for the
+    shapes the wrapper passes: a batch, the [None, :] view of one query, read-only input, an empty batch."""
+    from flatnav_b200.index import _ptr
+    a = np.arange(24, dtype=np.float32).reshape(6, 4)
+    assert _ptr(a) == a.ctypes.data
+    row = a[3][None, :]
+    assert row.flags.c_contiguous and _ptr(row) == row.ctypes.data == a.ctypes.data + 3 * 16
+    ro = a.copy()
+    ro.flags.writeable = False
+    assert _ptr(ro) == ro.ctypes.data
+    empty = np.empty((0, 4), dtype=np.float32)
+    assert _ptr(empty) == empty.ctypes.data
+    u8 = np.zeros((2, 32), dtype=np.uint8)
+    assert _ptr(u8) == u8.ctypes.data
