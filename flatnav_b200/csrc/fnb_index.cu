@@ -411,6 +411,17 @@ int plan_search(const fnb_index* ix, int64_t Q, int K, int ef, int ninit, Search
   const int sms = ix->replicas.empty() ? 148 : ix->replicas[0].num_sms;
   if (launch_q <= 0) launch_q = Q;
   p->lat = allow_latency_variant ? choose_latency_variant(launch_q, sms) : 0u;
+  // Two-hop prefetch of the CTA latency kernel: extra L2 fills that are free only while the batch leaves the memory
+  // system idle (FNB_PF2_MAXQ queries per launch, default 64; 0 disables)
+  static const long long pf2_maxq = [] {
+    const char* e = getenv("FNB_PF2_MAXQ");
+    return e ? atoll(e) : 64ll;
+  }();
+  static const long long pf2_minb = [] {  // lists shorter than this gain nothing (measured); the tests lower it
+    const char* e = getenv("FNB_PF2_MINB");
+    return e ? atoll(e) : 64ll;
+  }();
+  p->pf2 = (p->lat == 2u && launch_q <= pf2_maxq && (long long)p->B >= pf2_minb && h.M % 4 == 0) ? 1u : 0u;
   p->dense = p->lat ? 0u : choose_dense_plan(launch_q, sms, ix->G, cpl, p->B);
   if (p->lat == 2u)  // one query per CTA, up to 4 CTAs per SM: the visited set can have its full size
     size_visited(*p, env ? atoi(env) : 0, 4, 1);

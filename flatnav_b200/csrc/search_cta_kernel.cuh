@@ -36,23 +36,36 @@ __host__ __device__ constexpr int fnb_cta_batches(int g, int ch) {
   return want < cap ? want : cap;
 }
 
+__device__ __forceinline__ void distances_ready_arrive();
+
 // Rows ids[0..n) (shared memory), a quarter per worker warp: batch b (RPI rows) belongs to worker b % 4.  Same arithmetic
-// and reduction order as batch_distance.  Distances go to dist[0..n) in shared memory.
+// and reduction order as batch_distance.  Distances go to dist[0..n) in shared memory; the worker then ARRIVES at
+// "distances ready" itself, because of what may follow:
+// Two-hop prefetch (SearchParams::pf2, batches of a few queries on an otherwise idle GPU).  A row whose distance is
+// below the list's worst entry (hint_hi: its distance word as of the previous hop; 0 while the list is still filling,
+// when every row would qualify) enters the list and is likely to be expanded later.  After handing in its distances the
+// worker reads that node's links (an L2 hit: the driver prefetched the adjacency row when it filtered the link) and
+// prefetches the vector rows of ALL of them into L2, so that the hop which expands the node — the next one or the
+// twentieth — finds its rows in L2 instead of HBM.  A prefetch cannot change a result; the cost is ~16 KB of L2 fills
+// and ~130 requests on the SM's memory pipe per accepted candidate, off the critical path.
 template <int DT, int METRIC, int G, int CH, bool EXACT>
 __device__ __forceinline__ void cta_rows(const SearchParams& p, const uint4 (&q)[CH], const uint32_t* ids, uint32_t n,
-                                         float* dist, int worker, int lane) {
+                                         float* dist, int worker, int lane, uint32_t hint_hi) {
   typedef Arith<DT, METRIC> A;
   constexpr int RPI = 32 / G;
   constexpr int NB = fnb_cta_batches(G, CH);
   const int g = lane / G, pos = lane % G;
+  bool arrived = false;
   for (uint32_t b0 = (uint32_t)worker; b0 * RPI < n; b0 += FNB_CTA_WORKERS * NB) {
     uint4 x[NB][CH];
+    uint32_t rid[NB];
+    unsigned qual = 0;  // batches of this pass whose row (this lane's group) passes the hint
 #pragma unroll
     for (int u = 0; u < NB; u++) {
       const uint32_t c = (b0 + (uint32_t)u * FNB_CTA_WORKERS) * RPI + (uint32_t)g;
       const bool ok = c < n;
-      const uint32_t rid = ids[ok ? c : 0];
-      const uint4* row = p.vec + (size_t)rid * p.stride + pos;
+      rid[u] = ids[ok ? c : 0];
+      const uint4* row = p.vec + (size_t)rid[u] * p.stride + pos;
 #pragma unroll
       for (int k = 0; k < CH; k++) x[u][k] = ldg_stream_if(row + k * G, ok && (EXACT || (uint32_t)(k * G + pos) < p.nchunks));
     }
@@ -66,10 +79,34 @@ __device__ __forceinline__ void cta_rows(const SearchParams& p, const uint4 (&q)
           if (EXACT || (uint32_t)(k * G + pos) < p.nchunks) A::step(acc, q[k], x[u][k]);
 #pragma unroll
         for (int off = G / 2; off > 0; off >>= 1) acc = A::combine(acc, shfl_xor_t(acc, off));
-        if (pos == 0 && c < n) dist[c] = A::finish(acc);
+        const float d = A::finish(acc);  // every lane of the group holds the full sum
+        if (pos == 0 && c < n) dist[c] = d;
+        if (c < n && ord_f32(d) < hint_hi) qual |= 1u << u;
+      }
+    }
+    if ((b0 + FNB_CTA_WORKERS * NB) * RPI >= n) {  // warp-uniform: this worker's last pass of the round
+      distances_ready_arrive();
+      arrived = true;
+    }
+    if (p.pf2 && qual) {
+      const size_t row_bytes = (size_t)p.stride * FNB_CHUNK_BYTES;
+#pragma unroll
+      for (int u = 0; u < NB; u++) {
+        if (!((qual >> u) & 1u)) continue;
+        for (uint32_t o = (uint32_t)pos * 4u; o < p.M; o += 4u * G) {  // pf2 implies M % 4 == 0: 16-byte slices of the links
+          const uint4 a = __ldg(reinterpret_cast<const uint4*>(p.adj + (size_t)rid[u] * p.M + o));
+          const uint32_t nbv[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            if (nbv[j] == rid[u]) continue;  // unused link slot
+            const char* r = reinterpret_cast<const char*>(p.vec) + (size_t)nbv[j] * row_bytes;
+            for (uint32_t l = 0; l < p.lines_per_row; l++) prefetch_l2(r + (size_t)l * 128u);
+          }
+        }
       }
     }
   }
+  if (!arrived) distances_ready_arrive();  // no rows for this worker in this round
 }
 
 // Hand-off between the driver and the workers: two named barriers used as producer / consumer pairs (PTX bar.arrive /
@@ -189,11 +226,11 @@ __global__ void __launch_bounds__(FNB_CTA_WARPS * 32, 2) fnb_search_cta_kernel(c
         rows_published_wait();
         const uint32_t n = ctl[0];
         if (n == 0xffffffffu) break;
-        cta_rows<DT, METRIC, G, CH, EXACT>(p, q, ids, n, dist, warp - 1, lane);
-        distances_ready_arrive();
+        cta_rows<DT, METRIC, G, CH, EXACT>(p, q, ids, n, dist, warp - 1, lane, ctl[5]);  // (arrives at "distances ready")
       }
     } else {
       visited_clear(tab, p.vs_buckets, lane);
+      if (lane == 0) ctl[5] = 0u;  // two-hop prefetch hint: nothing qualifies during entry selection and while the list fills
       __syncwarp();
       if (p.N > 0) {
         // ---- entry selection: strided probes, first strict minimum wins (Index.h:845-870) ----
@@ -263,6 +300,7 @@ __global__ void __launch_bounds__(FNB_CTA_WARPS * 32, 2) fnb_search_cta_kernel(c
               const uint32_t worst_hi = (uint32_t)(list[len - 1] >> 32);
               pkey = make_key(fresh ? dist[myrank] : 0.f, nb);
               pacc = fresh && (!full || (uint32_t)(pkey >> 32) < worst_hi);
+              if (lane == 0) ctl[5] = full ? worst_hi : 0u;  // the workers' hint for the next round
             }
             __syncwarp();
           }

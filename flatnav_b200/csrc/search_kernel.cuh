@@ -100,6 +100,7 @@ struct SearchParams {
   uint32_t query_pitch_chunks;  // != 0 => queries are rows of a padded vector array with this pitch (construction:
                                 // the new nodes' own rows); chunks beyond the data are zero there
   uint32_t dense;  // 1 => the 28-warps-per-SM instantiation (large batches of short rows; never with lat)
+  uint32_t pf2;  // CTA latency kernel: two-hop prefetch (search_cta_kernel.cuh, cta_rows); set by the host for batches of a few queries
   uint32_t lat;  // latency variants (few queries; query = blockIdx.x, grid-stride, `counter` unused): 1 => one warp per
                  // CTA (fnb_search_kernel<.., LAT>), 2 => one CTA of four warps per query (search_cta_kernel.cuh)
   // Self-cleaning launch state (fnb_search_device): != null => the last warp of the grid to finish copies `totals` to

@@ -17,7 +17,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-ENV = {"cta": {"FNB_LAT": "2"}, "lat1": {"FNB_LAT": "1"}, "thr": {"FNB_LAT": "0", "FNB_DENSE": "0"},
+ENV = {"cta": {"FNB_LAT": "2", "FNB_PF2_MINB": "1"},  # (the two-hop prefetch also on the goldens' short lists) "lat1": {"FNB_LAT": "1"}, "thr": {"FNB_LAT": "0", "FNB_DENSE": "0"},
        "dense": {"FNB_LAT": "0", "FNB_DENSE": "1"}, "fed": {"FNB_LAT": "0"}}
 
 
