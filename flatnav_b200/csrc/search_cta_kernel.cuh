@@ -7,7 +7,9 @@
 // 3.1 us per hop against 1.7 us for one CPU thread of the reference.  Here six warps share one query, in three roles:
 //   * the driver (warp 0): pick, adjacency row, visited filter, acceptance test;
 //   * four workers (warps 1..4): fetch and evaluate the fresh rows of the expansion, a quarter each, every warp with ALL
-//     its rows in flight at once (registers are free at one CTA per query) — one HBM round trip per hop;
+//     its rows in flight at once (registers are free at one CTA per query) — one HBM round trip per hop; after handing
+//     in their distances they prefetch, into L2, the vectors of the links of every row that will enter the list
+//     (SearchParams::pf2, see cta_rows), so that the hop which expands it later is an L2 round trip;
 //   * the merge warp (warp 5): owns the sorted list — inserts the accepted candidates, hands back the list length and
 //     the first unexpanded entry.
 //   The hop is software-pipelined: the next node to expand is min(first unexpanded list entry, smallest accepted
